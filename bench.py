@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Physis b200 backend.
+
+Metric (BASELINE.json): 7-pt diffusion GLUP/s (+ Himeno GLUP/s as an extra key)
+and the achieved fraction of the measured HBM roofline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" is one full pass of the reference benchmark's hot path over one
+synthetic input: PSStencilRun of `--count` (default 1000, BASELINE config 2)
+7-pt sweeps on a 512^3 fp32 grid per GPU.
+  value : device-resident throughput (inputs already in HBM), all ranks
+  e2e   : the same through run_kernel_physis(): PSGridCopyin from pinned host
+          memory + the sweeps + PSGridCopyout, copies inside the timed region
+Timing is on the device (CUDA events on the runtime's stream, through the
+C ABI), max over ranks; the 1 GiB working set is far larger than the 126 MB L2.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _traffic(kernel):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(kernel)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _dist_setup(ngpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist_mod.init_process_group("nccl")
+        dist = dist_mod
+    return rank, world, dist
+
+
+def _max_over_ranks(dist, v):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _barrier(dist):
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------ reference arm
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (REFERENCE target) on host cores."""
+    if rank != 0:
+        return
+    import helpers as H
+    lib = H.oracle_ref()
+    kind = "reference"
+    if lib is None:
+        lib = H.oracle_port()
+        kind = "port"
+    n = args.size
+    sweeps = 2  # bounded sample: ~1 s per 512^3 sweep on one core
+    p = H.diffusion_params(n, n, n)
+    f0 = H.diffusion_initial(n, n, n, p)
+    lib.initialize_physis.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.initialize_physis(0, None, n, n, n)
+    lib.initialize_benchmark_physis(n, n, n)
+    lib.copyin_physis.argtypes = [C.c_void_p]
+    lib.copyin_physis(f0.ctypes.data)
+    lib.run_sweeps_only_physis.argtypes = [C.c_int] * 4 + [C.c_float] * 7
+    co = [float(c) for c in p[:7]]
+    for _ in range(args.warmup):
+        lib.run_sweeps_only_physis(sweeps, n, n, n, *co)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lib.run_sweeps_only_physis(sweeps, n, n, n, *co)
+    dt = time.perf_counter() - t0
+    lib.finalize_benchmark_physis()
+    glups = n ** 3 * sweeps * args.steps / dt / 1e9
+    sample = f"{sweeps} sweeps of {n}^3 per step, REFERENCE target (sequential codegen), 1 thread"
+    line = {
+        "impl": "reference", "metric": "7-pt diffusion GLUP/s", "value": glups, "unit": "GLUP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"7-pt 3D diffusion fp32 {n}^3 (BASELINE config 2 shape), "
+                               f"bounded sample of {sweeps} sweeps/step on host CPU"},
+        "cpu_baseline": {"value": glups, "unit": "GLUP/s", "cores": 1, "kind": kind,
+                         "sample": sample, "host_cores": os.cpu_count()},
+        "e2e": {"value": glups, "unit": "GLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------ b200 arm
+
+def cpu_baseline_sample():
+    """Config 1 (256^3, 100 sweeps) on one host core through the reference's REF runtime."""
+    import helpers as H
+    lib = H.oracle_ref()
+    kind = "reference"
+    if lib is None:
+        lib, kind = H.oracle_port(), "port"
+    n, sweeps = 256, 100
+    p = H.diffusion_params(n, n, n)
+    f0 = H.diffusion_initial(n, n, n, p)
+    lib.initialize_physis.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.initialize_physis(0, None, n, n, n)
+    lib.initialize_benchmark_physis(n, n, n)
+    lib.copyin_physis.argtypes = [C.c_void_p]
+    lib.copyin_physis(f0.ctypes.data)
+    lib.run_sweeps_only_physis.argtypes = [C.c_int] * 4 + [C.c_float] * 7
+    t0 = time.perf_counter()
+    lib.run_sweeps_only_physis(sweeps, n, n, n, *[float(c) for c in p[:7]])
+    dt = time.perf_counter() - t0
+    lib.finalize_benchmark_physis()
+    return {"value": n ** 3 * sweeps / dt / 1e9, "unit": "GLUP/s", "cores": 1, "kind": kind,
+            "host_cores": os.cpu_count(), "seconds": dt,
+            "sample": f"BASELINE config 1: {n}^3 fp32, {sweeps} sweeps, REFERENCE target "
+                      "(libphysis_rt_ref + translator-shaped sweep), 1 thread (REF codegen is sequential)"}
+
+
+def himeno_line(args, api, lib):
+    """Extra: Himeno XL (1024x512x512) with the residual emitted every sweep + PSReduce."""
+    mi, mj, mk = (1024, 512, 512) if args.himeno == "XL" else (512, 256, 256)
+    lib.himeno_init.argtypes = [C.c_int] * 3
+    lib.himeno_init(mi, mj, mk)
+    nn = args.himeno_nn
+    lib.himeno_sweeps_only.argtypes = [C.c_int, C.c_int]
+    lib.himeno_reduce_gosa.restype = C.c_float
+    out = {}
+    pts = (mi - 2) * (mj - 2) * (mk - 2)
+    for with_gosa in (0, 1):
+        for _ in range(2):
+            lib.himeno_sweeps_only(nn, with_gosa)
+        api.rt().__PSB200TimerStart()
+        lib.himeno_sweeps_only(nn, with_gosa)
+        gosa = lib.himeno_reduce_gosa() if with_gosa else 0.0
+        ms = api.rt().__PSB200TimerStopMs()
+        bpl = 64 if with_gosa else 56
+        key = "with_residual" if with_gosa else "sweep_only"
+        out[key] = {"glups": pts * nn / ms / 1e6, "ms_per_sweep": ms / nn,
+                    "alg_bytes_per_lup": bpl, "gbs": pts * nn * bpl / ms / 1e6}
+        if with_gosa:
+            out[key]["gosa"] = float(gosa)
+    lib.himeno_finalize()
+    out["size"] = f"{mi}x{mj}x{mk}"
+    out["sweeps"] = nn
+    return out
+
+
+def run_b200(args, rank, world, dist):
+    import physis_b200
+    from physis_b200 import api
+    import helpers as H
+
+    if world > 1:
+        raise SystemExit("multi-GPU bench path not wired yet in this revision")
+
+    lib = physis_b200.load_programs()
+    n, count = args.size, args.count
+    npts = n ** 3
+    # synthetic initial field of the benchmark's shape (smooth cosine product)
+    ax = (1.0 - np.cos(2 * np.pi * (np.arange(n, dtype=np.float64) + 0.5) / n)).astype(np.float32)
+    f0 = (0.125 * ax[:, None, None] * ax[None, :, None] * ax[None, None, :]).astype(np.float32).ravel()
+    co = [0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.4]
+
+    lib.initialize_physis.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.initialize_physis(0, None, n, n, n)
+    for kv in args.opt:
+        api.set_option(kv)
+    lib.initialize_benchmark_physis(n, n, n)
+    lib.copyin_physis.argtypes = [C.c_void_p]
+    lib.copyout_physis.argtypes = [C.c_void_p]
+    lib.run_sweeps_only_physis.argtypes = [C.c_int] * 4 + [C.c_float] * 7
+    lib.run_kernel_physis.argtypes = [C.c_int, C.c_void_p] + [C.c_int] * 3 + [C.c_float] * 7
+    r = api.rt()
+
+    host, host_ptr = api.pinned_empty(npts * 4, np.float32)
+    host[:] = f0
+    lib.copyin_physis(host.ctypes.data)
+
+    # ---- value: device-resident sweeps --------------------------------------
+    for _ in range(args.warmup):
+        lib.run_sweeps_only_physis(count, n, n, n, *co)
+    r.__PSB200Synchronize()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    _barrier(dist)
+    r.__PSB200ResetStats()
+    r.__PSB200TimerStart()
+    for _ in range(args.steps):
+        lib.run_sweeps_only_physis(count, n, n, n, *co)
+    ms = r.__PSB200TimerStopMs()
+    _barrier(dist)
+    st = api.stats()
+    launches = int(st.kernel_launches)
+    ms = _max_over_ranks(dist, ms)
+    clocks = sampler.stop()
+    value = npts * count * args.steps * world / ms / 1e6  # GLUP/s
+
+    # ---- e2e: copyin (pinned host) + sweeps + copyout per step --------------
+    for _ in range(min(args.warmup, 2)):
+        lib.run_kernel_physis(count, host.ctypes.data, n, n, n, *co)
+    host[:] = f0
+    _barrier(dist)
+    r.__PSB200TimerStart()
+    for _ in range(args.steps):
+        lib.run_kernel_physis(count, host.ctypes.data, n, n, n, *co)
+    ms_e2e = r.__PSB200TimerStopMs()
+    _barrier(dist)
+    ms_e2e = _max_over_ranks(dist, ms_e2e)
+    e2e = npts * count * args.steps * world / ms_e2e / 1e6
+    checksum = float(np.sum(host[::4097], dtype=np.float64))
+
+    # ---- roofline of the dominant kernel --------------------------------------
+    peak, peak_src = _peaks()
+    alg_bytes = 8 * npts                      # 1 fp32 read + 1 fp32 write per point per launch
+    launch_ms = ms / max(launches, 1)
+    achieved = alg_bytes / launch_ms / 1e6     # GB/s
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": _traffic("Star7Kernel<float>"),
+                "kernel": "Star7Kernel<float>", "alg_bytes_per_launch": alg_bytes,
+                "launch_ms": launch_ms, "peak_source": peak_src}
+
+    lib.finalize_benchmark_physis()
+    r.__PSB200HostFree(C.c_void_p(host_ptr))
+
+    line = {
+        "metric": "7-pt diffusion GLUP/s", "value": value, "unit": "GLUP/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"7-pt 3D diffusion fp32 {n}^3 per GPU, {count} sweeps per step "
+                               "(BASELINE config 2)",
+                   "l2": f"working set {2 * npts * 4 / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
+                   "options": args.opt},
+        "e2e": {"value": e2e, "unit": "GLUP/s", "h2d_bytes_per_step": npts * 4,
+                "d2h_bytes_per_step": npts * 4, "ms_per_step": ms_e2e / args.steps,
+                "checksum": checksum},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_himeno:
+        line["himeno"] = himeno_line(args, api, lib)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--count", type=int, default=1000)
+    ap.add_argument("--opt", action="append", default=[], help="runtime option key=value")
+    ap.add_argument("--no-himeno", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--himeno", default="XL")
+    ap.add_argument("--himeno-nn", type=int, default=20)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    rank, world, dist = _dist_setup(args.gpus)
+    run_b200(args, rank, world, dist)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,172 @@
+/*
+ * Hand-emitted `b200`-target translation of this repo's
+ *   examples/dsl/diffusion3d_periodic_staggered.c   (BASELINE config 5)
+ * User type `struct Cell {double p, q;}`: SoA on the device, so the generic
+ * kernels see `struct __PSGrid3DCell_dev { int dim[3]; double *p; double *q; }`
+ * (the layout translator/cuda_runtime_builder.cc:351-391 generates), which
+ * overlays the runtime's device view.  Entry points match
+ * oracle/programs/diffusion3d_periodic_staggered.ref.c.
+ */
+#define PHYSIS_B200
+#include "physis/physis.h"
+#include "physis/physis_b200_generic.cuh"
+
+struct Cell {
+  double p;
+  double q;
+};
+struct __PSGrid3DCell_dev {
+  int dim[3];
+  double *p;
+  double *q;
+};
+
+#define KGETD(g, x, y, z) ((g)->p[__PSGridGetOffset3DDev((g), (x), (y), (z))])
+
+__device__ static inline void step_pq(const int x, const int y, const int z,
+                                      __PSGrid3DCell_dev *u, __PSGrid3DDouble_dev *kap) {
+  double c = u->p[__PSGridGetOffsetPeriodic3DDev(u, x, y, z)];
+  double w = u->p[__PSGridGetOffsetPeriodic3DDev(u, x-1, y, z)];
+  double e = u->p[__PSGridGetOffsetPeriodic3DDev(u, x+1, y, z)];
+  double n = u->p[__PSGridGetOffsetPeriodic3DDev(u, x, y-1, z)];
+  double s = u->p[__PSGridGetOffsetPeriodic3DDev(u, x, y+1, z)];
+  double b = u->p[__PSGridGetOffsetPeriodic3DDev(u, x, y, z-1)];
+  double t = u->p[__PSGridGetOffsetPeriodic3DDev(u, x, y, z+1)];
+  double k = 0.125 * (KGETD(kap, x, y, z) + KGETD(kap, x+1, y, z)
+                      + KGETD(kap, x, y+1, z) + KGETD(kap, x, y, z+1)
+                      + KGETD(kap, x+1, y+1, z) + KGETD(kap, x+1, y, z+1)
+                      + KGETD(kap, x, y+1, z+1) + KGETD(kap, x+1, y+1, z+1));
+  u->q[__PSGridGetOffset3DDev(u, x, y, z)] = c + k * (w + e + n + s + b + t - 6.0 * c);
+}
+
+__device__ static inline void step_qp(const int x, const int y, const int z,
+                                      __PSGrid3DCell_dev *u, __PSGrid3DDouble_dev *kap) {
+  double c = u->q[__PSGridGetOffsetPeriodic3DDev(u, x, y, z)];
+  double w = u->q[__PSGridGetOffsetPeriodic3DDev(u, x-1, y, z)];
+  double e = u->q[__PSGridGetOffsetPeriodic3DDev(u, x+1, y, z)];
+  double n = u->q[__PSGridGetOffsetPeriodic3DDev(u, x, y-1, z)];
+  double s = u->q[__PSGridGetOffsetPeriodic3DDev(u, x, y+1, z)];
+  double b = u->q[__PSGridGetOffsetPeriodic3DDev(u, x, y, z-1)];
+  double t = u->q[__PSGridGetOffsetPeriodic3DDev(u, x, y, z+1)];
+  double k = 0.125 * (KGETD(kap, x, y, z) + KGETD(kap, x+1, y, z)
+                      + KGETD(kap, x, y+1, z) + KGETD(kap, x, y, z+1)
+                      + KGETD(kap, x+1, y+1, z) + KGETD(kap, x+1, y, z+1)
+                      + KGETD(kap, x, y+1, z+1) + KGETD(kap, x+1, y+1, z+1));
+  u->p[__PSGridGetOffset3DDev(u, x, y, z)] = c + k * (w + e + n + s + b + t - 6.0 * c);
+}
+
+struct __PSStencil_step_pq { PSDomain3D dom; __PSGrid *u; int u_index; __PSGrid *kap; int kap_index; };
+struct __PSStencil_step_qp { PSDomain3D dom; __PSGrid *u; int u_index; __PSGrid *kap; int kap_index; };
+
+static struct __PSStencil_step_pq __PSStencilMap_step_pq(PSDomain3D dom, __PSGrid *u, __PSGrid *kap) {
+  struct __PSStencil_step_pq stencil = {dom, u, __PSGridGetID(u), kap, __PSGridGetID(kap)};
+  return stencil;
+}
+static struct __PSStencil_step_qp __PSStencilMap_step_qp(PSDomain3D dom, __PSGrid *u, __PSGrid *kap) {
+  struct __PSStencil_step_qp stencil = {dom, u, __PSGridGetID(u), kap, __PSGridGetID(kap)};
+  return stencil;
+}
+
+__global__ void __PSStencilRun_step_pq(__PSDomain dom, int zchunk, __PSGrid3DCell_dev u,
+                                       __PSGrid3DDouble_dev kap) {
+  __PSB200_FOREACH_POINT_BEGIN(dom, zchunk, x, y, z)
+    step_pq(x, y, z, &u, &kap);
+  __PSB200_FOREACH_POINT_END
+}
+__global__ void __PSStencilRun_step_qp(__PSDomain dom, int zchunk, __PSGrid3DCell_dev u,
+                                       __PSGrid3DDouble_dev kap) {
+  __PSB200_FOREACH_POINT_BEGIN(dom, zchunk, x, y, z)
+    step_qp(x, y, z, &u, &kap);
+  __PSB200_FOREACH_POINT_END
+}
+
+static void __PSStencilLaunch_step_pq(const void *sv, __PSB200Stream stream) {
+  const struct __PSStencil_step_pq *s = (const struct __PSStencil_step_pq *)sv;
+  __PSB200GenericShape sh = __PSB200GenericShapeFor(&s->dom, 3);
+  __PSStencilRun_step_pq<<<sh.grid, sh.block, 0, (cudaStream_t)stream>>>(
+      s->dom, sh.zchunk, *((__PSGrid3DCell_dev *)(s->u->dev)),
+      *((__PSGrid3DDouble_dev *)(s->kap->dev)));
+}
+static void __PSStencilLaunch_step_qp(const void *sv, __PSB200Stream stream) {
+  const struct __PSStencil_step_qp *s = (const struct __PSStencil_step_qp *)sv;
+  __PSB200GenericShape sh = __PSB200GenericShapeFor(&s->dom, 3);
+  __PSStencilRun_step_qp<<<sh.grid, sh.block, 0, (cudaStream_t)stream>>>(
+      s->dom, sh.zchunk, *((__PSGrid3DCell_dev *)(s->u->dev)),
+      *((__PSGrid3DDouble_dev *)(s->kap->dev)));
+}
+
+static int g_force_generic = 0;
+
+static float __PSStencilRun_0(int iter, struct __PSStencil_step_pq s0, struct __PSStencil_step_qp s1) {
+  __PSB200StencilDesc d[2];
+  memset(d, 0, sizeof(d));
+  for (int i = 0; i < 2; ++i) {
+    d[i].kind = g_force_generic ? PSB200_KIND_GENERIC : PSB200_KIND_PERIODIC7_STAGGERED;
+    d[i].elm_type = PS_DOUBLE;
+    d[i].num_grids = 2;
+  }
+  d[0].dom = s0.dom; d[0].grids[0] = s0.u; d[0].grids[1] = s0.kap;
+  d[0].members[0] = 0; d[0].members[1] = 1;  /* read .p, emit .q */
+  d[0].stencil = &s0; d[0].launch = __PSStencilLaunch_step_pq; d[0].name = "step_pq";
+  d[1].dom = s1.dom; d[1].grids[0] = s1.u; d[1].grids[1] = s1.kap;
+  d[1].members[0] = 1; d[1].members[1] = 0;  /* read .q, emit .p */
+  d[1].stencil = &s1; d[1].launch = __PSStencilLaunch_step_qp; d[1].name = "step_qp";
+  return __PSB200StencilRun(iter, 2, d);
+}
+
+static __PSGrid *u;
+static __PSGrid *kap;
+
+extern "C" {
+
+void pstag_init(int argc, char **argv, int nx, int ny, int nz) {
+  PSInit(&argc, &argv, 3, nx + 1, ny + 1, nz + 1);
+  {
+    PSVectorInt dims = {nx, ny, nz};
+    __PSGridTypeMemberInfo member_info[2];
+    member_info[0].type = PS_DOUBLE;
+    member_info[0].size = sizeof(double);
+    member_info[0].rank = 0;
+    member_info[1].type = PS_DOUBLE;
+    member_info[1].size = sizeof(double);
+    member_info[1].rank = 0;
+    __PSGridTypeInfo type_info = {PS_USER, sizeof(struct Cell), 2, member_info};
+    u = __PSGridNew(&type_info, 3, dims, NULL);
+  }
+  {
+    PSVectorInt dims = {nx + 1, ny + 1, nz + 1};
+    __PSGridTypeInfo type_info = {PS_DOUBLE, sizeof(double), 0, NULL};
+    kap = __PSGridNew(&type_info, 3, dims, NULL);
+  }
+}
+
+void pstag_force_generic(int on) { g_force_generic = on; }
+
+void pstag_run(int count, struct Cell *u_host, const double *kap_host,
+               int nx, int ny, int nz) {
+  PSDomain3D dom = PSDomain3DNew(0, nx, 0, ny, 0, nz);
+  __PSGridCopyin(u, u_host, NULL);
+  __PSGridCopyin(kap, kap_host, NULL);
+  __PSStencilRun_0(count / 2, __PSStencilMap_step_pq(dom, u, kap),
+                   __PSStencilMap_step_qp(dom, u, kap));
+  __PSGridCopyout(u, u_host, NULL);
+}
+
+void pstag_copyin(const struct Cell *u_host, const double *kap_host) {
+  __PSGridCopyin(u, u_host, NULL);
+  __PSGridCopyin(kap, kap_host, NULL);
+}
+void pstag_sweeps_only(int count, int nx, int ny, int nz) {
+  PSDomain3D dom = PSDomain3DNew(0, nx, 0, ny, 0, nz);
+  __PSStencilRun_0(count / 2, __PSStencilMap_step_pq(dom, u, kap),
+                   __PSStencilMap_step_qp(dom, u, kap));
+}
+void pstag_copyout(struct Cell *u_host) { __PSGridCopyout(u, u_host, NULL); }
+
+void pstag_finalize(void) {
+  __PSGridFree(u, NULL);
+  __PSGridFree(kap, NULL);
+  PSFinalize();
+}
+
+}  // extern "C"

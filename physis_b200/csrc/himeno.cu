@@ -1,0 +1,359 @@
+// Himeno 19-point Jacobi sweep — hand-written sm_100a kernel.
+//
+// One sweep of examples/himeno/himenobmtxpa_physis.c:331-361 (jacobi_kernel):
+//   s0 = a0*p(k+1) + a1*p(j+1) + a2*p(i+1)
+//      + b0*(p(j+1,k+1) - p(j-1,k+1) - p(j+1,k-1) + p(j-1,k-1))
+//      + b1*(p(i+1,j+1) - p(i+1,j-1) - p(i-1,j+1) + p(i-1,j-1))
+//      + b2*(p(i+1,k+1) - p(i+1,k-1) - p(i-1,k+1) + p(i-1,k-1))
+//      + c0*p(k-1) + c1*p(j-1) + c2*p(i-1) + wrk1
+//   ss = (s0*a3 - p)*bnd;   p1 = p + omega*ss          [; gosa_g = ss*ss]
+// with i = x (fastest), j = y, k = z, on the interior domain.  All operations
+// are separately rounded fp32 in C's left-to-right order (no FMA), so the result
+// is bit-identical to the REFERENCE target.  The `_GOSA` form additionally
+// emits ss*ss (examples/dsl/himeno_gosa.c), the DSL spelling of the original
+// benchmark's residual (himenobmtxpa_original.c:334).
+//
+// Traffic per point: 12 coefficient/source streams + p read + p1 write = 56 B
+// (himenobmtxpa_physis.c:418-432), +4 B with the residual emit.  HBM-bound.
+//  * p0: haloed xy tiles of planes z-1, z, z+1 through the same TMA /
+//    mbarrier shared-memory ring as star7.cu (zero fill outside the grid; those
+//    values only reach points outside the domain, which are never stored);
+//  * the 12 coefficient arrays are pure streams: one 128-bit read-only load per
+//    thread per array, issued before the thread waits on the p planes, so ~200 B
+//    per thread are in flight;
+//  * 128-bit stores; vectors straddling the domain edge store element-wise.
+#include "runtime.h"
+#include "tma.cuh"
+#include "sweep_common.cuh"
+
+#include <algorithm>
+#include <string>
+
+namespace physis_b200 {
+
+namespace {
+
+using namespace sweep;
+
+struct HimenoArgs {
+  const float *a0, *a1, *a2, *a3, *b0, *b1, *b2, *c0, *c1, *c2, *bnd, *wrk1;
+  float *p1;
+  float *gosa;  // nullptr unless the _GOSA form
+  float omega;
+  int nx, ny, nz;
+  int dx0, dx1, dy0, dy1, dz0, dz1;
+  int xbase;
+  int ntx, nty, nzc, zc, nitems;
+  int stages;
+};
+
+__device__ __forceinline__ float4 LdStream(const float *p) {
+  return __ldcs(reinterpret_cast<const float4 *>(p));
+}
+
+// One output point.  pXYZ naming: m = -1, c = 0, p = +1 for (x, y, z).
+__device__ __forceinline__ float Jacobi(float a0, float a1, float a2, float a3, float b0,
+                                        float b1, float b2, float c0, float c1, float c2,
+                                        float bnd, float wrk1, float omega,
+                                        float ccc, float ccp, float cpc, float pcc, float cpp,
+                                        float cmp, float cpm, float cmm, float ppc, float pmc,
+                                        float mpc, float mmc, float pcp, float pcm, float mcp,
+                                        float mcm, float ccm, float cmc, float mcc, float *ss_out) {
+  float s0 = MulRn(a0, ccp);
+  s0 = AddRn(s0, MulRn(a1, cpc));
+  s0 = AddRn(s0, MulRn(a2, pcc));
+  s0 = AddRn(s0, MulRn(b0, AddRn(SubRn(SubRn(cpp, cmp), cpm), cmm)));
+  s0 = AddRn(s0, MulRn(b1, AddRn(SubRn(SubRn(ppc, pmc), mpc), mmc)));
+  s0 = AddRn(s0, MulRn(b2, AddRn(SubRn(SubRn(pcp, pcm), mcp), mcm)));
+  s0 = AddRn(s0, MulRn(c0, ccm));
+  s0 = AddRn(s0, MulRn(c1, cmc));
+  s0 = AddRn(s0, MulRn(c2, mcc));
+  s0 = AddRn(s0, wrk1);
+  const float ss = MulRn(SubRn(MulRn(s0, a3), ccc), bnd);
+  *ss_out = ss;
+  return AddRn(ccc, MulRn(omega, ss));
+}
+
+// TY rows per CTA tile, one row per consumer warp, one box (128 floats) wide.
+template <int TY, bool GOSA>
+__global__ void __launch_bounds__((TY + 1) * 32)
+HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ HimenoArgs a) {
+  using G = Geom<float>;
+  constexpr int VEC = 4;
+  constexpr int NW = TY;
+  constexpr int ROWB = G::ROW_BYTES;
+  constexpr int STAGE_BYTES = BoxStride<float, TY>();
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *empty = full + kMaxStages;
+  unsigned char *planes = smem + kBarrierBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = a.stages;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      tma::mbar_init(&full[s], 1);
+      tma::mbar_init(&empty[s], NW);
+    }
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int tiles_xy = a.ntx * a.nty;
+
+  if (warp == NW) {
+    if (lane != 0) return;
+    tma::prefetch_tensormap(&tmap);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      const int zci = item / tiles_xy;
+      const int txy = item - zci * tiles_xy;
+      const int ty = txy / a.ntx;
+      const int tx = txy - ty * a.ntx;
+      const int x0 = a.xbase + tx * G::TXB;
+      const int y0 = a.dy0 + ty * TY;
+      const int zb = a.dz0 + zci * a.zc;
+      const int ze = min(zb + a.zc, a.dz1);
+      // the domain is interior in z (checked on the host): planes zb-1 .. ze exist
+      for (int z = zb - 1; z <= ze; ++z) {
+        tma::mbar_wait(&empty[stage], phase ^ 1u);
+        tma::mbar_arrive_expect_tx(&full[stage], (uint32_t)((TY + 2) * ROWB));
+        tma::load_3d(planes + stage * STAGE_BYTES, &tmap, &full[stage], x0 - G::HX, y0 - 1, z);
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  const int col_off = (G::HX + lane * VEC) * (int)sizeof(float);
+  int stage = 0;
+  uint32_t phase = 0;
+  auto next_of = [&](int st) { return (st + 1 == S) ? 0 : st + 1; };
+  auto release = [&](int st) {
+    __syncwarp();
+    if (lane == 0) tma::mbar_arrive(&empty[st]);
+  };
+
+  for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+    const int zci = item / tiles_xy;
+    const int txy = item - zci * tiles_xy;
+    const int ty = txy / a.ntx;
+    const int tx = txy - ty * a.ntx;
+    const int x = a.xbase + tx * G::TXB + lane * VEC;
+    const int y = a.dy0 + ty * TY + warp;
+    const int zb = a.dz0 + zci * a.zc;
+    const int ze = min(zb + a.zc, a.dz1);
+    const bool row_ok = (y < a.dy1) && (x < a.nx);
+    // per-element store mask
+    bool ok[VEC];
+    bool all_ok = row_ok;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      ok[j] = row_ok && (x + j >= a.dx0) && (x + j < a.dx1);
+      all_ok = all_ok && ok[j];
+    }
+    bool any_ok = false;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) any_ok = any_ok || ok[j];
+
+    // ring positions of planes z-1 (sb), z (sc), z+1 (st)
+    int sb = stage;
+    uint32_t phb = phase;
+    tma::mbar_wait(&full[sb], phb);
+    int sc = next_of(sb);
+    uint32_t phc = (sc == 0) ? (phb ^ 1u) : phb;
+    tma::mbar_wait(&full[sc], phc);
+
+    for (int z = zb; z < ze; ++z) {
+      const size_t g = ((size_t)z * a.ny + y) * a.nx + x;
+      float4 va0, va1, va2, va3, vb0, vb1, vb2, vc0, vc1, vc2, vbnd, vwrk;
+      if (any_ok) {
+        va0 = LdStream(a.a0 + g); va1 = LdStream(a.a1 + g); va2 = LdStream(a.a2 + g);
+        va3 = LdStream(a.a3 + g); vb0 = LdStream(a.b0 + g); vb1 = LdStream(a.b1 + g);
+        vb2 = LdStream(a.b2 + g); vc0 = LdStream(a.c0 + g); vc1 = LdStream(a.c1 + g);
+        vc2 = LdStream(a.c2 + g); vbnd = LdStream(a.bnd + g); vwrk = LdStream(a.wrk1 + g);
+      }
+      const int st = next_of(sc);
+      const uint32_t pht = (st == 0) ? (phc ^ 1u) : phc;
+      tma::mbar_wait(&full[st], pht);
+
+      const unsigned char *pb = planes + sb * STAGE_BYTES + (warp + 1) * ROWB;
+      const unsigned char *pc = planes + sc * STAGE_BYTES + (warp + 1) * ROWB;
+      const unsigned char *pt = planes + st * STAGE_BYTES + (warp + 1) * ROWB;
+      auto vec = [&](const unsigned char *row, int dy) {
+        return *reinterpret_cast<const float4 *>(row + dy * ROWB + col_off);
+      };
+      auto west = [&](const unsigned char *row, int dy) {
+        return *reinterpret_cast<const float *>(row + dy * ROWB + col_off - 4);
+      };
+      auto east = [&](const unsigned char *row, int dy) {
+        return *reinterpret_cast<const float *>(row + dy * ROWB + col_off + 16);
+      };
+      if (any_ok) {
+        // plane z
+        const float4 c_c = vec(pc, 0), c_n = vec(pc, -1), c_s = vec(pc, 1);
+        const float c_cw = west(pc, 0), c_ce = east(pc, 0);
+        const float c_nw = west(pc, -1), c_ne = east(pc, -1);
+        const float c_sw = west(pc, 1), c_se = east(pc, 1);
+        // plane z-1 and z+1: 5-point star
+        const float4 b_c = vec(pb, 0), b_n = vec(pb, -1), b_s = vec(pb, 1);
+        const float b_w = west(pb, 0), b_e = east(pb, 0);
+        const float4 t_c = vec(pt, 0), t_n = vec(pt, -1), t_s = vec(pt, 1);
+        const float t_w = west(pt, 0), t_e = east(pt, 0);
+
+        float4 o, q;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          // x-1 / x+1 values in each needed row
+          const float c_xm = (j == 0) ? c_cw : Elem(c_c, j - 1);
+          const float c_xp = (j == VEC - 1) ? c_ce : Elem(c_c, j + 1);
+          const float n_xm = (j == 0) ? c_nw : Elem(c_n, j - 1);
+          const float n_xp = (j == VEC - 1) ? c_ne : Elem(c_n, j + 1);
+          const float s_xm = (j == 0) ? c_sw : Elem(c_s, j - 1);
+          const float s_xp = (j == VEC - 1) ? c_se : Elem(c_s, j + 1);
+          const float b_xm = (j == 0) ? b_w : Elem(b_c, j - 1);
+          const float b_xp = (j == VEC - 1) ? b_e : Elem(b_c, j + 1);
+          const float t_xm = (j == 0) ? t_w : Elem(t_c, j - 1);
+          const float t_xp = (j == VEC - 1) ? t_e : Elem(t_c, j + 1);
+          float ss;
+          const float v = Jacobi(
+              Elem(va0, j), Elem(va1, j), Elem(va2, j), Elem(va3, j), Elem(vb0, j), Elem(vb1, j),
+              Elem(vb2, j), Elem(vc0, j), Elem(vc1, j), Elem(vc2, j), Elem(vbnd, j), Elem(vwrk, j),
+              a.omega,
+              /*ccc*/ Elem(c_c, j), /*ccp*/ Elem(t_c, j), /*cpc*/ Elem(c_s, j), /*pcc*/ c_xp,
+              /*cpp*/ Elem(t_s, j), /*cmp*/ Elem(t_n, j), /*cpm*/ Elem(b_s, j), /*cmm*/ Elem(b_n, j),
+              /*ppc*/ s_xp, /*pmc*/ n_xp, /*mpc*/ s_xm, /*mmc*/ n_xm,
+              /*pcp*/ t_xp, /*pcm*/ b_xp, /*mcp*/ t_xm, /*mcm*/ b_xm,
+              /*ccm*/ Elem(b_c, j), /*cmc*/ Elem(c_n, j), /*mcc*/ c_xm, &ss);
+          SetElem(o, j, v);
+          SetElem(q, j, MulRn(ss, ss));
+        }
+        if (all_ok) {
+          *reinterpret_cast<float4 *>(a.p1 + g) = o;
+          if (GOSA) *reinterpret_cast<float4 *>(a.gosa + g) = q;
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            if (ok[j]) {
+              a.p1[g + j] = Elem(o, j);
+              if (GOSA) a.gosa[g + j] = Elem(q, j);
+            }
+          }
+        }
+      }
+      // plane z-1 is no longer needed
+      release(sb);
+      sb = sc; phb = phc;
+      sc = st; phc = pht;
+    }
+    // planes ze-1 (sb) and ze (sc) were loaded for this item and are still held
+    release(sb);
+    release(sc);
+    // the next item's first plane follows `sc` in the ring
+    stage = next_of(sc);
+    phase = (stage == 0) ? (phc ^ 1u) : phc;
+  }
+}
+
+template <int TY>
+size_t SmemBytes(int stages) {
+  return kBarrierBytes + (size_t)stages * BoxStride<float, TY>();
+}
+
+}  // namespace
+
+struct HimenoPlan {
+  int grid = 0, block = 0;
+  size_t smem = 0;
+  CUtensorMap tmap;
+  HimenoArgs args;
+  const void *fn = nullptr;
+};
+
+HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string *why) {
+  const bool gosa = d.kind == PSB200_KIND_HIMENO19_GOSA;
+  const int ng = gosa ? 15 : 14;
+  if (d.num_grids != ng || d.num_scalars != 1) { *why = "expects 14(+1) grids and omega"; return nullptr; }
+  Grid *g[15];
+  for (int i = 0; i < ng; ++i) {
+    g[i] = Grid::FromHandle(d.grids[i]);
+    if (g[i]->num_dims != 3 || g[i]->type != PS_FLOAT) { *why = "3-D float grids only"; return nullptr; }
+    for (int k = 0; k < 3; ++k)
+      if (g[i]->dim[k] != g[0]->dim[k]) { *why = "grids must have equal extents"; return nullptr; }
+  }
+  if (g[0] == g[1]) { *why = "in-place sweep"; return nullptr; }
+  const int nx = g[0]->dim[0], ny = g[0]->dim[1], nz = g[0]->dim[2];
+  const __PSDomain &dom = d.dom;
+  if (nx % 4 != 0) { *why = "x extent must be a multiple of 4"; return nullptr; }
+  // every read p(x±1, y±1, z±1) must stay inside the grid
+  if (dom.local_min[0] < 1 || dom.local_max[0] > nx - 1 || dom.local_min[1] < 1 ||
+      dom.local_max[1] > ny - 1 || dom.local_min[2] < 1 || dom.local_max[2] > nz - 1) {
+    *why = "domain must be interior (19-point reach)";
+    return nullptr;
+  }
+  if (dom.local_max[0] <= dom.local_min[0] || dom.local_max[1] <= dom.local_min[1] ||
+      dom.local_max[2] <= dom.local_min[2]) { *why = "empty domain"; return nullptr; }
+
+  HimenoPlan *p = new HimenoPlan();
+  constexpr int TY = 8;
+  p->fn = gosa ? (const void *)HimenoKernel<TY, true> : (const void *)HimenoKernel<TY, false>;
+  int stages = 5;
+  p->smem = SmemBytes<TY>(stages);
+  p->block = (TY + 1) * 32;
+  PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+  int occ = 0;
+  PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->fn, p->block, p->smem));
+  PSB_CHECK(occ > 0, "himeno kernel does not fit on an SM");
+
+  HimenoArgs &a = p->args;
+  const float **coef[] = {&a.a0, &a.a1, &a.a2, &a.a3, &a.b0, &a.b1, &a.b2, &a.c0, &a.c1, &a.c2,
+                          &a.bnd, &a.wrk1};
+  // descriptor grid order = kernel parameter order: p0,p1,a0..a3,b0..b2,c0..c2,bnd,wrk1[,gosa]
+  for (int i = 0; i < 12; ++i) *coef[i] = (const float *)g[2 + i]->members[0].dev;
+  a.p1 = (float *)g[1]->members[0].dev;
+  a.gosa = gosa ? (float *)g[14]->members[0].dev : nullptr;
+  a.omega = (float)d.scalars[0];
+  a.nx = nx; a.ny = ny; a.nz = nz;
+  a.dx0 = dom.local_min[0]; a.dx1 = dom.local_max[0];
+  a.dy0 = dom.local_min[1]; a.dy1 = dom.local_max[1];
+  a.dz0 = dom.local_min[2]; a.dz1 = dom.local_max[2];
+  a.xbase = a.dx0 / 4 * 4;
+  a.ntx = CeilDiv(a.dx1 - a.xbase, Geom<float>::TXB);
+  a.nty = CeilDiv(a.dy1 - a.dy0, TY);
+  const int nzd = a.dz1 - a.dz0;
+  const int slots = rt->sm_count * occ;
+  int zc = rt->opt.himeno_zc;
+  if (zc <= 0) {
+    int tiles = a.ntx * a.nty;
+    int want_chunks = std::max(1, CeilDiv(2L * slots, tiles));
+    zc = std::max(8, CeilDiv(nzd, want_chunks));
+    zc = std::min(zc, nzd);
+  }
+  a.zc = zc;
+  a.nzc = CeilDiv(nzd, zc);
+  a.nitems = a.ntx * a.nty * a.nzc;
+  a.stages = stages;
+  p->grid = std::min(a.nitems, slots);
+
+  int dimv[3] = {nx, ny, nz};
+  int boxv[3] = {Geom<float>::BW, TY + 2, 1};
+  if (!EncodeTensorMap3D(&p->tmap, TmaElem::F32, g[0]->members[0].dev, dimv, boxv)) {
+    *why = "grid shape violates a TMA constraint";
+    delete p;
+    return nullptr;
+  }
+  return p;
+}
+
+void LaunchHimeno(Runtime *rt, HimenoPlan *p) {
+  void *args[2] = {&p->tmap, &p->args};
+  PSB_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(p->block), args, p->smem, rt->stream));
+}
+
+void DestroyHimeno(HimenoPlan *p) { delete p; }
+
+}  // namespace physis_b200

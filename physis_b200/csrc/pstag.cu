@@ -1,0 +1,383 @@
+// Periodic 7-point update of one member of a user-defined point type with a
+// vertex-staggered coefficient grid — hand-written sm_100a kernel (fp64).
+//
+// One sweep of examples/dsl/diffusion3d_periodic_staggered.c (BASELINE config 5):
+//   k   = 0.125 * (kap(x,y,z) + kap(x+1,y,z) + kap(x,y+1,z) + kap(x,y,z+1)
+//                  + kap(x+1,y+1,z) + kap(x+1,y,z+1) + kap(x,y+1,z+1) + kap(x+1,y+1,z+1))
+//   out = c + k * (w + e + n + s + b + t - 6.0*c)
+// where c,w,e,n,s,b,t are PSGridGetPeriodic reads of member `rd` of u and `out`
+// is PSGridEmitUtype into member `wr` of the same grid; kap is (N+1)^3.  It
+// composes what the reference tests one at a time:
+//   tests/system_tests/test_cases/test_user-defined-type-7-pt-periodic.c:19-27,
+//   test_7-pt-double-type.c:17-25, examples/test_staggered_grid.c:6-14.
+// Arithmetic is separately rounded fp64 in source order (bit-exact vs REF).
+//
+// Device layout: user types are SoA, so the sweep reads one 8-byte member array
+// and writes another: 16 B/LUP + 8 B/LUP for the kap stream = 24 B/LUP (AoS
+// would move 40).  Structure as star7.cu — persistent CTAs, TMA ring of xy
+// tiles along z, register z-window, shuffles for x-neighbours, 128-bit stores —
+// plus the periodic wrap done by the producer: the tile's interior rows, its
+// two y-halo rows and (for tiles touching x=0 / x=nx-1) a 16-byte-wide wrap
+// column are separate TMA boxes, and z wraps in the plane coordinate.  kap's row
+// pitch ((N+1)*8 bytes) is not a multiple of 16, so it cannot be a TMA tensor;
+// it is read with coalesced 8-byte loads (each value reused from L1 by the 8
+// cells around it) and carried from plane z+1 to z in registers.
+#include "runtime.h"
+#include "tma.cuh"
+#include "sweep_common.cuh"
+
+#include <algorithm>
+#include <string>
+
+namespace physis_b200 {
+
+namespace {
+
+using namespace sweep;
+
+struct PstagArgs {
+  double *out;
+  const double *kap;
+  int nx, ny, nz;     // cell grid
+  int kx, ky;         // kap pitches (nx+1, ny+1)
+  int dx0, dx1, dy0, dy1, dz0, dz1;
+  int ntx, nty, nzc, zc, nitems;
+  int stages;
+};
+
+__host__ __device__ constexpr int Up128(int v) { return (v + 127) / 128 * 128; }
+
+// Shared-memory layout of one box of one ring stage.  Every TMA destination
+// must be 128-byte aligned, so the pieces are separate regions:
+//   [MAIN: TY rows][NORTH halo row][SOUTH halo row][WEST wrap col][EAST wrap col]
+template <int TY>
+struct PstagLayout {
+  static constexpr int ROWB = Geom<double>::ROW_BYTES;
+  static constexpr int NORTH = Up128(TY * ROWB);
+  static constexpr int SOUTH = NORTH + Up128(ROWB);
+  static constexpr int WEST = SOUTH + Up128(ROWB);
+  static constexpr int EAST = WEST + Up128(TY * 16);
+  static constexpr int STRIDE = EAST + Up128(TY * 16);
+};
+template <int TY>
+constexpr int PstagBoxStride() { return PstagLayout<TY>::STRIDE; }
+
+template <int TY, int RY, int NBX>
+__global__ void __launch_bounds__((NBX * (TY / RY) + 1) * 32)
+PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant__ CUtensorMap map_row,
+            const __grid_constant__ CUtensorMap map_col, const __grid_constant__ PstagArgs a) {
+  using G = Geom<double>;
+  constexpr int VEC = 2;
+  constexpr int NWY = TY / RY;
+  constexpr int NW = NBX * NWY;
+  constexpr int ROWB = G::ROW_BYTES;            // 544
+  using L = PstagLayout<TY>;
+  constexpr int BOX_STRIDE = L::STRIDE;
+  constexpr int STAGE_BYTES = NBX * BOX_STRIDE;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *empty = full + kMaxStages;
+  unsigned char *planes = smem + kBarrierBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = a.stages;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      tma::mbar_init(&full[s], 1);
+      tma::mbar_init(&empty[s], NW);
+    }
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int tiles_xy = a.ntx * a.nty;
+
+  if (warp == NW) {
+    if (lane != 0) return;
+    tma::prefetch_tensormap(&map_main);
+    tma::prefetch_tensormap(&map_row);
+    tma::prefetch_tensormap(&map_col);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      const int zci = item / tiles_xy;
+      const int txy = item - zci * tiles_xy;
+      const int ty = txy / a.ntx;
+      const int tx = txy - ty * a.ntx;
+      const int x0 = tx * (NBX * G::TXB);
+      const int y0 = a.dy0 + ty * TY;
+      const int zb = a.dz0 + zci * a.zc;
+      const int ze = min(zb + a.zc, a.dz1);
+      const int yn = (y0 - 1 + a.ny) % a.ny;   // periodic halo rows
+      const int ys = (y0 + TY) % a.ny;
+      uint32_t tx_bytes = 0;
+#pragma unroll
+      for (int b = 0; b < NBX; ++b) {
+        const int bx0 = x0 + b * G::TXB;
+        if (bx0 >= a.nx) continue;
+        tx_bytes += (uint32_t)((TY + 2) * ROWB);
+        if (bx0 == 0) tx_bytes += TY * 16;
+        if (bx0 + G::TXB >= a.nx) tx_bytes += TY * 16;
+      }
+      for (int zz = zb - 1; zz <= ze; ++zz) {
+        const int z = (zz + a.nz) % a.nz;
+        tma::mbar_wait(&empty[stage], phase ^ 1u);
+        tma::mbar_arrive_expect_tx(&full[stage], tx_bytes);
+        unsigned char *dst = planes + stage * STAGE_BYTES;
+#pragma unroll
+        for (int b = 0; b < NBX; ++b) {
+          const int bx0 = x0 + b * G::TXB;
+          if (bx0 >= a.nx) continue;
+          unsigned char *bd = dst + b * BOX_STRIDE;
+          tma::load_3d(bd, &map_main, &full[stage], bx0 - G::HX, y0, z);
+          tma::load_3d(bd + L::NORTH, &map_row, &full[stage], bx0 - G::HX, yn, z);
+          tma::load_3d(bd + L::SOUTH, &map_row, &full[stage], bx0 - G::HX, ys, z);
+          if (bx0 == 0)
+            tma::load_3d(bd + L::WEST, &map_col, &full[stage], a.nx - G::HX, y0, z);
+          if (bx0 + G::TXB >= a.nx)
+            tma::load_3d(bd + L::EAST, &map_col, &full[stage], 0, y0, z);
+        }
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  const int bx = warp % NBX;
+  const int wy = warp / NBX;
+  const int col_off = (G::HX + lane * VEC) * (int)sizeof(double);
+  const int row0 = wy * RY;  // first own row inside the MAIN region
+  const int north_off = (wy == 0) ? L::NORTH : (row0 - 1) * ROWB;
+  const int south_off = (wy == NWY - 1) ? L::SOUTH : (row0 + RY) * ROWB;
+
+  int stage = 0;
+  uint32_t phase = 0;
+  auto advance = [&]() {
+    if (++stage == S) { stage = 0; phase ^= 1u; }
+  };
+  auto release = [&](int st) {
+    __syncwarp();
+    if (lane == 0) tma::mbar_arrive(&empty[st]);
+  };
+
+  for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+    const int zci = item / tiles_xy;
+    const int txy = item - zci * tiles_xy;
+    const int ty = txy / a.ntx;
+    const int tx = txy - ty * a.ntx;
+    const int bx0 = tx * (NBX * G::TXB) + bx * G::TXB;
+    const int x = bx0 + lane * VEC;
+    const int ybase = a.dy0 + ty * TY + wy * RY;
+    const int zb = a.dz0 + zci * a.zc;
+    const int ze = min(zb + a.zc, a.dz1);
+    const bool x_ok = (x >= a.dx0) && (x + VEC <= a.dx1);
+    const bool x_first = (x == 0);
+    const bool x_last = (x + VEC == a.nx);
+    const bool in_grid = x < a.nx;
+
+    const unsigned char *box = planes + bx * BOX_STRIDE;
+    double2 cen[RY], bot[RY], top[RY];
+    // kap values at plane z (lo) and z+1 (hi): rows ybase .. ybase+RY, x .. x+2
+    double klo[RY + 1][3], khi[RY + 1][3];
+
+    auto load_kap = [&](double (&k)[RY + 1][3], int z) {
+#pragma unroll
+      for (int r = 0; r <= RY; ++r) {
+        const int y = min(ybase + r, a.ky - 1);
+        const double *row = a.kap + ((size_t)z * a.ky + y) * a.kx;
+        const int xx = min(x, a.kx - 2);
+        const double v0 = __ldg(row + xx), v1 = __ldg(row + xx + 1);
+        double v2 = __shfl_down_sync(0xffffffffu, v0, 1);
+        if (lane == 31 || x + VEC >= a.nx) v2 = __ldg(row + min(xx + 2, a.kx - 1));
+        k[r][0] = v0; k[r][1] = v1; k[r][2] = v2;
+      }
+    };
+
+    // plane zb-1 -> bot
+    tma::mbar_wait(&full[stage], phase);
+    {
+      const unsigned char *p = box + stage * STAGE_BYTES + row0 * ROWB + col_off;
+#pragma unroll
+      for (int r = 0; r < RY; ++r) bot[r] = *reinterpret_cast<const double2 *>(p + r * ROWB);
+    }
+    release(stage);
+    advance();
+    int stage_c = stage;
+    tma::mbar_wait(&full[stage], phase);
+    {
+      const unsigned char *p = box + stage * STAGE_BYTES + row0 * ROWB + col_off;
+#pragma unroll
+      for (int r = 0; r < RY; ++r) cen[r] = *reinterpret_cast<const double2 *>(p + r * ROWB);
+    }
+    advance();
+    load_kap(klo, zb);
+
+    for (int z = zb; z < ze; ++z) {
+      load_kap(khi, z + 1);
+      const int stage_t = stage;
+      tma::mbar_wait(&full[stage], phase);
+      {
+        const unsigned char *p = box + stage * STAGE_BYTES + row0 * ROWB + col_off;
+#pragma unroll
+        for (int r = 0; r < RY; ++r) top[r] = *reinterpret_cast<const double2 *>(p + r * ROWB);
+      }
+      const unsigned char *cb = box + stage_c * STAGE_BYTES;
+      const double2 north = *reinterpret_cast<const double2 *>(cb + north_off + col_off);
+      const double2 south = *reinterpret_cast<const double2 *>(cb + south_off + col_off);
+#pragma unroll
+      for (int r = 0; r < RY; ++r) {
+        const int y = ybase + r;
+        const double2 c = cen[r];
+        double wv = __shfl_up_sync(0xffffffffu, c.y, 1);
+        double ev = __shfl_down_sync(0xffffffffu, c.x, 1);
+        const unsigned char *rowp = cb + (row0 + r) * ROWB;
+        if (lane == 0) wv = *reinterpret_cast<const double *>(rowp + (G::HX - 1) * sizeof(double));
+        if (lane == 31) ev = *reinterpret_cast<const double *>(rowp + (G::HX + G::TXB) * sizeof(double));
+        // periodic wrap in x: the wrap columns hold x = nx-2,nx-1 (west) and x = 0,1 (east)
+        if (x_first) wv = *reinterpret_cast<const double *>(cb + L::WEST + (row0 + r) * 16 + 8);
+        if (x_last) ev = *reinterpret_cast<const double *>(cb + L::EAST + (row0 + r) * 16);
+        const double2 nv = (r == 0) ? north : cen[r - 1];
+        const double2 sv = (r == RY - 1) ? south : cen[r + 1];
+        const double2 bv = bot[r], tv = top[r];
+        double2 o;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const double cj = Elem(c, j);
+          const double wj = (j == 0) ? wv : c.x;
+          const double ej = (j == VEC - 1) ? ev : c.y;
+          // 0.125 * (k000 + k100 + k010 + k001 + k110 + k101 + k011 + k111)
+          double ks = AddRn(klo[r][j], klo[r][j + 1]);
+          ks = AddRn(ks, klo[r + 1][j]);
+          ks = AddRn(ks, khi[r][j]);
+          ks = AddRn(ks, klo[r + 1][j + 1]);
+          ks = AddRn(ks, khi[r][j + 1]);
+          ks = AddRn(ks, khi[r + 1][j]);
+          ks = AddRn(ks, khi[r + 1][j + 1]);
+          const double k = MulRn(0.125, ks);
+          // w + e + n + s + b + t - 6.0*c
+          double acc = AddRn(wj, ej);
+          acc = AddRn(acc, Elem(nv, j));
+          acc = AddRn(acc, Elem(sv, j));
+          acc = AddRn(acc, Elem(bv, j));
+          acc = AddRn(acc, Elem(tv, j));
+          acc = SubRn(acc, MulRn(6.0, cj));
+          SetElem(o, j, AddRn(cj, MulRn(k, acc)));
+        }
+        if (x_ok && in_grid && y >= a.dy0 && y < a.dy1) {
+          double2 *dst = reinterpret_cast<double2 *>(a.out + ((size_t)z * a.ny + y) * a.nx + x);
+          *dst = o;
+        }
+      }
+      release(stage_c);
+      stage_c = stage_t;
+      advance();
+#pragma unroll
+      for (int r = 0; r < RY; ++r) {
+        bot[r] = cen[r];
+        cen[r] = top[r];
+      }
+#pragma unroll
+      for (int r = 0; r <= RY; ++r) {
+        klo[r][0] = khi[r][0]; klo[r][1] = khi[r][1]; klo[r][2] = khi[r][2];
+      }
+    }
+    release(stage_c);
+  }
+}
+
+constexpr int kTY = 16, kRY = 2, kNBX = 2;
+
+}  // namespace
+
+struct PstagPlan {
+  int grid = 0, block = 0;
+  size_t smem = 0;
+  CUtensorMap map_main, map_row, map_col;
+  PstagArgs args;
+  const void *fn = nullptr;
+};
+
+PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *why) {
+  if (d.num_grids != 2) { *why = "expects grids {u, kap}"; return nullptr; }
+  Grid *u = Grid::FromHandle(d.grids[0]);
+  Grid *kap = Grid::FromHandle(d.grids[1]);
+  if (u->num_dims != 3 || kap->num_dims != 3) { *why = "3-D grids only"; return nullptr; }
+  if (!u->is_user_type() || kap->type != PS_DOUBLE) { *why = "u must be a user type, kap double"; return nullptr; }
+  const int rd = d.members[0], wr = d.members[1];
+  if (rd < 0 || wr < 0 || rd >= (int)u->members.size() || wr >= (int)u->members.size() || rd == wr) {
+    *why = "needs distinct read/write members"; return nullptr;
+  }
+  const MemberLayout &mr = u->members[rd], &mw = u->members[wr];
+  if (mr.type != PS_DOUBLE || mw.type != PS_DOUBLE || mr.count != 1 || mw.count != 1) {
+    *why = "members must be scalar doubles"; return nullptr;
+  }
+  const int nx = u->dim[0], ny = u->dim[1], nz = u->dim[2];
+  for (int i = 0; i < 3; ++i)
+    if (kap->dim[i] != u->dim[i] + 1) { *why = "kap must be one larger than u per dimension"; return nullptr; }
+  const __PSDomain &dom = d.dom;
+  if (nx % 2 != 0 || dom.local_min[0] % 2 != 0 || dom.local_max[0] % 2 != 0) {
+    *why = "x extent and domain x-range must be even"; return nullptr;
+  }
+  if (ny % kTY != 0 || (dom.local_min[1] % kTY) != 0) { *why = "y extent must be a multiple of the tile height"; return nullptr; }
+  if (nx < Geom<double>::HX || nz < 1) { *why = "grid too small"; return nullptr; }
+  for (int i = 0; i < 3; ++i)
+    if (dom.local_min[i] < 0 || dom.local_max[i] > u->dim[i] || dom.local_max[i] <= dom.local_min[i]) {
+      *why = "bad domain"; return nullptr;
+    }
+  if (dom.local_min[0] != 0) { *why = "domain must start at x = 0"; return nullptr; }
+
+  PstagPlan *p = new PstagPlan();
+  p->fn = (const void *)PstagKernel<kTY, kRY, kNBX>;
+  const int stages = 4;
+  p->smem = kBarrierBytes + (size_t)stages * kNBX * PstagBoxStride<kTY>();
+  p->block = (kNBX * (kTY / kRY) + 1) * 32;
+  PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+  int occ = 0;
+  PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->fn, p->block, p->smem));
+  PSB_CHECK(occ > 0, "pstag kernel does not fit on an SM");
+
+  PstagArgs &a = p->args;
+  a.out = (double *)mw.dev;
+  a.kap = (const double *)kap->members[0].dev;
+  a.nx = nx; a.ny = ny; a.nz = nz;
+  a.kx = kap->dim[0]; a.ky = kap->dim[1];
+  a.dx0 = dom.local_min[0]; a.dx1 = dom.local_max[0];
+  a.dy0 = dom.local_min[1]; a.dy1 = dom.local_max[1];
+  a.dz0 = dom.local_min[2]; a.dz1 = dom.local_max[2];
+  a.ntx = CeilDiv(a.dx1, (long)kNBX * Geom<double>::TXB);
+  a.nty = CeilDiv(a.dy1 - a.dy0, kTY);
+  const int nzd = a.dz1 - a.dz0;
+  const int slots = rt->sm_count * occ;
+  const int tiles = a.ntx * a.nty;
+  const int want_chunks = std::max(1, CeilDiv(2L * slots, tiles));
+  a.zc = std::min(nzd, std::max(8, CeilDiv(nzd, want_chunks)));
+  a.nzc = CeilDiv(nzd, a.zc);
+  a.nitems = tiles * a.nzc;
+  a.stages = stages;
+  p->grid = std::min(a.nitems, slots);
+
+  int dimv[3] = {nx, ny, nz};
+  int box_main[3] = {Geom<double>::BW, kTY, 1};
+  int box_row[3] = {Geom<double>::BW, 1, 1};
+  int box_col[3] = {Geom<double>::HX, kTY, 1};
+  if (!EncodeTensorMap3D(&p->map_main, TmaElem::F64, mr.dev, dimv, box_main) ||
+      !EncodeTensorMap3D(&p->map_row, TmaElem::F64, mr.dev, dimv, box_row) ||
+      !EncodeTensorMap3D(&p->map_col, TmaElem::F64, mr.dev, dimv, box_col)) {
+    *why = "grid shape violates a TMA constraint";
+    delete p;
+    return nullptr;
+  }
+  return p;
+}
+
+void LaunchPstag(Runtime *rt, PstagPlan *p) {
+  void *args[4] = {&p->map_main, &p->map_row, &p->map_col, &p->args};
+  PSB_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(p->block), args, p->smem, rt->stream));
+}
+
+void DestroyPstag(PstagPlan *p) { delete p; }
+
+}  // namespace physis_b200

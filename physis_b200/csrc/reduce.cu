@@ -1,0 +1,183 @@
+// PSReduce on the b200 target: whole-grid MAX/MIN/SUM/PROD of a primitive-type
+// grid into one host scalar.
+//
+// Replaces runtime/reduce_cuda.{h,cu} (thrust::reduce / max_element /
+// min_element, reduce_cuda.h:19-40) and, for the single-GPU case, the CUB
+// two-stage kernels of runtime/reduce_grid_mpi_cuda_exp.cu:176-328.  Semantics
+// follow the REFERENCE target (runtime/libphysis_rt_ref.cc:19-30): every one of
+// the num_elms elements takes part, the result has the grid's element type.
+// MAX/MIN use true identities (lowest/highest), not the reference CUDA
+// runtime's FLT_MIN (runtime/reduce.h:61-63), which is wrong for all-negative
+// data; REF seeds with d[0] and is right — we agree with REF.
+//
+// Shape: stage 1 — persistent grid (a multiple of the SM count), each thread
+// folds 16-byte vector loads in a grid-stride loop, warp shuffle tree, one
+// shared-memory hop across warps, one partial per block; stage 2 — a single
+// block folds the partials in a fixed order.  The combine order depends only on
+// (num_elms, launch shape), so results are run-to-run deterministic.  Integer
+// results are exact (wrap-around like the CPU's two's-complement adds);
+// floating SUM/PROD differ from REF's sequential left fold by reassociation
+// only (tests bound it; exactly-representable data is bit-identical).
+#include "runtime.h"
+
+#include <cfloat>
+#include <climits>
+
+namespace physis_b200 {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { using type = float4; static constexpr int N = 4; };
+template <> struct Vec16<int> { using type = int4; static constexpr int N = 4; };
+template <> struct Vec16<double> { using type = double2; static constexpr int N = 2; };
+template <> struct Vec16<long> { using type = longlong2; static constexpr int N = 2; };
+
+template <typename T> __host__ __device__ inline T Lowest();
+template <> __host__ __device__ inline float Lowest<float>() { return -INFINITY; }
+template <> __host__ __device__ inline double Lowest<double>() { return -INFINITY; }
+template <> __host__ __device__ inline int Lowest<int>() { return INT_MIN; }
+template <> __host__ __device__ inline long Lowest<long>() { return LONG_MIN; }
+template <typename T> __host__ __device__ inline T Highest();
+template <> __host__ __device__ inline float Highest<float>() { return INFINITY; }
+template <> __host__ __device__ inline double Highest<double>() { return INFINITY; }
+template <> __host__ __device__ inline int Highest<int>() { return INT_MAX; }
+template <> __host__ __device__ inline long Highest<long>() { return LONG_MAX; }
+
+template <typename T> struct Unsigned { using type = T; };
+template <> struct Unsigned<int> { using type = unsigned int; };
+template <> struct Unsigned<long> { using type = unsigned long; };
+
+template <typename T, int OP>
+struct Op {
+  __host__ __device__ static T identity() {
+    if (OP == PS_MAX) return Lowest<T>();
+    if (OP == PS_MIN) return Highest<T>();
+    if (OP == PS_SUM) return (T)0;
+    return (T)1;
+  }
+  __device__ static T apply(T x, T y) {
+    using U = typename Unsigned<T>::type;
+    if (OP == PS_MAX) return (x > y) ? x : y;
+    if (OP == PS_MIN) return (x < y) ? x : y;
+    if (OP == PS_SUM) return (T)((U)x + (U)y);
+    return (T)((U)x * (U)y);
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ T ShflDown(T v, int d) {
+  return __shfl_down_sync(0xffffffffu, v, d);
+}
+template <>
+__device__ __forceinline__ long ShflDown<long>(long v, int d) {
+  return (long)__shfl_down_sync(0xffffffffu, (long long)v, d);
+}
+
+template <typename T, int OP>
+__device__ __forceinline__ T BlockFold(T v) {
+  __shared__ T warp_part[kThreads / 32];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = Op<T, OP>::apply(v, ShflDown(v, d));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_part[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = (lane < kThreads / 32) ? warp_part[lane] : Op<T, OP>::identity();
+#pragma unroll
+    for (int d = 4; d > 0; d >>= 1) v = Op<T, OP>::apply(v, ShflDown(v, d));
+  }
+  return v;  // valid in thread 0
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(kThreads)
+ReduceStage1(const T *__restrict__ data, long n, T *__restrict__ partials) {
+  using V = typename Vec16<T>::type;
+  constexpr int N = Vec16<T>::N;
+  T acc = Op<T, OP>::identity();
+  const long nvec = n / N;
+  const V *vdata = reinterpret_cast<const V *>(data);
+  const long stride = (long)gridDim.x * kThreads;
+  long i = (long)blockIdx.x * kThreads + threadIdx.x;
+  // 4 independent 16-byte loads in flight per thread
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    V v0 = __ldg(vdata + i), v1 = __ldg(vdata + i + stride), v2 = __ldg(vdata + i + 2 * stride),
+      v3 = __ldg(vdata + i + 3 * stride);
+    const T *e0 = reinterpret_cast<const T *>(&v0), *e1 = reinterpret_cast<const T *>(&v1),
+            *e2 = reinterpret_cast<const T *>(&v2), *e3 = reinterpret_cast<const T *>(&v3);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      acc = Op<T, OP>::apply(acc, e0[k]);
+      acc = Op<T, OP>::apply(acc, e1[k]);
+      acc = Op<T, OP>::apply(acc, e2[k]);
+      acc = Op<T, OP>::apply(acc, e3[k]);
+    }
+  }
+  for (; i < nvec; i += stride) {
+    V v0 = __ldg(vdata + i);
+    const T *e0 = reinterpret_cast<const T *>(&v0);
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc = Op<T, OP>::apply(acc, e0[k]);
+  }
+  // scalar tail (n not a multiple of the vector width)
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - nvec * N))
+    acc = Op<T, OP>::apply(acc, data[nvec * N + threadIdx.x]);
+  acc = BlockFold<T, OP>(acc);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(kThreads)
+ReduceStage2(const T *__restrict__ partials, int n, T *__restrict__ out) {
+  T acc = Op<T, OP>::identity();
+  for (int i = threadIdx.x; i < n; i += kThreads) acc = Op<T, OP>::apply(acc, partials[i]);
+  acc = BlockFold<T, OP>(acc);
+  if (threadIdx.x == 0) *out = acc;
+}
+
+template <typename T, int OP>
+void Run(Runtime *rt, const Grid &g, void *out_host) {
+  const long n = (long)g.num_elms;
+  constexpr int N = Vec16<T>::N;
+  long want = (n / N + (long)kThreads * 4 - 1) / ((long)kThreads * 4);
+  int blocks = (int)std::max<long>(1, std::min<long>(want, (long)rt->sm_count * 8));
+  DeviceBuffer &scr = rt->small_scratch(sizeof(T) * (size_t)(blocks + 1));
+  T *partials = (T *)scr.get();
+  T *result = partials + blocks;
+  ReduceStage1<T, OP><<<blocks, kThreads, 0, rt->stream>>>((const T *)g.members[0].dev, n, partials);
+  ReduceStage2<T, OP><<<1, kThreads, 0, rt->stream>>>(partials, blocks, result);
+  PSB_CUDA(cudaGetLastError());
+  rt->stats.kernel_launches += 2;
+  PSB_CUDA(cudaMemcpyAsync(out_host, result, sizeof(T), cudaMemcpyDeviceToHost, rt->stream));
+  PSB_CUDA(cudaStreamSynchronize(rt->stream));
+  rt->stats.d2h_bytes += sizeof(T);
+}
+
+template <typename T>
+void Dispatch(Runtime *rt, const Grid &g, PSReduceOp op, void *out) {
+  switch (op) {
+    case PS_MAX: Run<T, PS_MAX>(rt, g, out); break;
+    case PS_MIN: Run<T, PS_MIN>(rt, g, out); break;
+    case PS_SUM: Run<T, PS_SUM>(rt, g, out); break;
+    case PS_PROD: Run<T, PS_PROD>(rt, g, out); break;
+    default: PSAbort(1);
+  }
+}
+
+}  // namespace
+
+void ReduceGrid(Runtime *rt, const Grid &g, PSType type, PSReduceOp op, void *out_host) {
+  PSB_CHECK(g.num_elms > 0, "PSReduce on an empty grid");
+  switch (type) {
+    case PS_FLOAT: Dispatch<float>(rt, g, op, out_host); break;
+    case PS_DOUBLE: Dispatch<double>(rt, g, op, out_host); break;
+    case PS_INT: Dispatch<int>(rt, g, op, out_host); break;
+    case PS_LONG: Dispatch<long>(rt, g, op, out_host); break;
+    default: PSB_CHECK(false, "PSReduce: unsupported element type");
+  }
+}
+
+}  // namespace physis_b200

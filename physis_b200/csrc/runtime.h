@@ -1,0 +1,178 @@
+// Internal object model of the b200 runtime (host side, C++17).
+//
+// Replaces, for the `b200` target, the reference's
+//   runtime/buffer.{h,cc}, buffer_cuda.{h,cu}   -> DeviceBuffer / PinnedBuffer
+//   runtime/grid.{h,cc} (Grid, GridSpace)        -> Grid / GridSpace
+//   runtime/runtime_cuda.h, libphysis_rt_cuda.cc -> Runtime + the C entry points
+// It is not a translation of those classes: one device allocation per struct
+// member (SoA), pinned double-buffered staging for host<->device traffic, a
+// single explicit stream pair instead of the default stream, and no virtual
+// Buffer hierarchy.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "physis/physis_b200.h"
+#include "common.h"
+
+namespace physis_b200 {
+
+// Device allocation with grow-only capacity (semantics of Buffer::EnsureCapacity,
+// runtime/buffer.cc:22-35: reallocate when the request reaches the actual size,
+// otherwise only the logical size changes).  Fresh memory is zero-filled like
+// BufferCUDADev (runtime/buffer_cuda.cu:106-117).
+class DeviceBuffer {
+ public:
+  DeviceBuffer() = default;
+  ~DeviceBuffer() { Free(); }
+  DeviceBuffer(const DeviceBuffer &) = delete;
+  DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+  // Returns false on out-of-memory (the caller decides whether that is fatal).
+  bool Allocate(size_t bytes, cudaStream_t stream);
+  void EnsureCapacity(size_t bytes, cudaStream_t stream);
+  void Free();
+  void *get() const { return ptr_; }
+  size_t size() const { return size_; }
+  size_t capacity() const { return capacity_; }
+
+ private:
+  void *ptr_ = nullptr;
+  size_t size_ = 0;
+  size_t capacity_ = 0;
+};
+
+// Page-locked host staging (role of BufferCUDAHost, runtime/buffer_cuda.cu:12-52).
+class PinnedBuffer {
+ public:
+  PinnedBuffer() = default;
+  ~PinnedBuffer() { Free(); }
+  PinnedBuffer(const PinnedBuffer &) = delete;
+  PinnedBuffer &operator=(const PinnedBuffer &) = delete;
+  void EnsureCapacity(size_t bytes);
+  void Free();
+  void *get() const { return ptr_; }
+  size_t capacity() const { return capacity_; }
+
+ private:
+  void *ptr_ = nullptr;
+  size_t capacity_ = 0;
+};
+
+struct MemberLayout {
+  PSType type = PS_FLOAT;
+  int size = 0;          // bytes of one scalar of this member
+  int count = 1;         // array members: product of dims
+  int aos_offset = 0;    // byte offset inside the host struct
+  void *dev = nullptr;   // device array [count][num_elms] (SoA; arrays plane-major)
+};
+
+// One Physis grid.  `handle` is what the generated code holds (its address is
+// the `__PSGrid*`); everything else is runtime-private.
+class Grid {
+ public:
+  __PSGrid handle;            // must stay first: Grid* <-> __PSGrid* casts
+  int id = 0;
+  PSType type = PS_FLOAT;
+  int num_dims = 0;
+  int dim[PS_MAX_DIM] = {1, 1, 1};
+  int64_t num_elms = 0;
+  int elm_size = 0;
+  std::vector<MemberLayout> members;   // size 1 for primitive grids
+  std::vector<DeviceBuffer *> storage; // one per member
+  void *dev_view = nullptr;            // host copy of the by-value device view
+  bool external_dev = false;           // allocated by a generated devNew function
+
+  bool is_user_type() const { return type == PS_USER; }
+  size_t bytes() const { return (size_t)elm_size * (size_t)num_elms; }
+  static Grid *FromHandle(void *h) { return reinterpret_cast<Grid *>(h); }
+};
+
+// id -> grid registry (role of GridSpace, runtime/grid.h:73-119).
+class GridSpace {
+ public:
+  ~GridSpace();
+  Grid *Create(const __PSGridTypeInfo *ti, int num_dims, const int *dim, cudaStream_t stream);
+  void Destroy(Grid *g);
+  Grid *Find(int id) const;
+  size_t live() const { return grids_.size(); }
+
+ private:
+  std::map<int, Grid *> grids_;
+  int next_id_ = 1;
+};
+
+struct Options {
+  // star-7 sweep tile shape (see star7.cu); 0 = automatic
+  int star7_ty = 0, star7_ry = 0, star7_nbx = 0, star7_stages = 0, star7_zc = 0, star7_occ = 0;
+  int star7_variant = 0, star7_l2hint = 0, star7_sthint = 0;
+  int himeno_by = 0, himeno_zc = 0;
+  int time_kernels = 0;        // per-family CUDA-event timing (for bench roofline)
+  size_t stage_chunk = 32u << 20;  // pinned staging chunk for pageable copies
+};
+
+class Runtime {
+ public:
+  static Runtime *Get();          // aborts if PSInit has not run
+  static Runtime *GetOrNull();
+  static void Create(int *argc, char ***argv);
+  static void Destroy();
+
+  int device = 0;
+  int sm_count = 0;
+  size_t l2_bytes = 0;
+  cudaStream_t stream = nullptr;       // compute + ordered copies
+  cudaStream_t copy_stream = nullptr;  // second DMA queue for pipelined staging
+  GridSpace gs;
+  Options opt;
+  __PSB200Stats stats{};
+
+  // kernel timing (opt.time_kernels): accumulated device ms + launches of the
+  // family last run through __PSB200StencilRun
+  double timed_ms = 0.0;
+  uint64_t timed_launches = 0;
+
+  // Host<->device transfers of logically contiguous bytes.  Pageable host
+  // memory is pipelined through two pinned chunks so the CPU memcpy overlaps
+  // the DMA; pinned/registered host memory goes straight to cudaMemcpyAsync.
+  void CopyToDevice(void *dst, const void *src, size_t bytes);
+  void CopyToHost(void *dst, const void *src, size_t bytes);
+  DeviceBuffer &scratch(size_t bytes);        // device staging for AoS<->SoA transposes
+  DeviceBuffer &small_scratch(size_t bytes);  // reduction partials
+
+  cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
+
+ private:
+  Runtime() = default;
+  ~Runtime();
+  PinnedBuffer pinned_[2];
+  cudaEvent_t pinned_free_[2] = {nullptr, nullptr};
+  DeviceBuffer scratch_;
+  DeviceBuffer small_scratch_;
+};
+
+// ---- kernels (defined in the .cu files) ---------------------------------
+
+// AoS (host struct order) <-> SoA (one array per member) on the device.
+void LaunchAosToSoa(const Grid &g, const void *aos_dev, cudaStream_t s);
+void LaunchSoaToAos(const Grid &g, void *aos_dev, cudaStream_t s);
+
+// PSReduce: whole-grid reduction of a primitive-type grid to one host scalar.
+void ReduceGrid(Runtime *rt, const Grid &g, PSType type, PSReduceOp op, void *out_host);
+
+// Specialised sweeps.  Each returns false if the descriptor does not satisfy the
+// kernel's preconditions (then the caller reports a fatal error: there is no
+// slower fallback for a specialised kind other than the program supplying a
+// GENERIC launch stub).
+struct SweepPlan;  // opaque per-descriptor prepared state
+SweepPlan *PrepareSweep(Runtime *rt, const __PSB200StencilDesc &d);
+void LaunchSweep(Runtime *rt, SweepPlan *plan);
+void DestroySweep(SweepPlan *plan);
+const char *SweepName(const SweepPlan *plan);
+
+}  // namespace physis_b200
