@@ -236,5 +236,4 @@ def pinned_empty(nbytes, dtype=np.uint8):
     p = rt().__PSB200HostAlloc(nbytes)
     buf = (C.c_uint8 * nbytes).from_address(p)
     a = np.frombuffer(buf, dtype=dtype)
-    a._physis_pinned_base = p  # noqa: keep the address for host_free
     return a, p
