@@ -299,15 +299,31 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
       dom.local_max[2] <= dom.local_min[2]) { *why = "empty domain"; return nullptr; }
 
   HimenoPlan *p = new HimenoPlan();
-  constexpr int TY = 8;
-  p->fn = gosa ? (const void *)HimenoKernel<TY, true> : (const void *)HimenoKernel<TY, false>;
-  int stages = 5;
-  p->smem = SmemBytes<TY>(stages);
+  // rows per CTA tile = consumer warps; +1 producer warp.  Warps are allocated in
+  // groups of four, so 7+1 (two CTAs per SM) and 15+1 fill the register file where
+  // 8+1 strands three warps' worth.
+  int TY = rt->opt.himeno_by;
+  if (TY != 7 && TY != 8 && TY != 11 && TY != 15) TY = 7;
+  int stages = rt->opt.himeno_stages > 0 ? std::min(rt->opt.himeno_stages, kMaxStages) : 5;
+  if (stages < 4) stages = 4;
+  switch (TY) {
+    case 7: p->fn = gosa ? (const void *)HimenoKernel<7, true> : (const void *)HimenoKernel<7, false>;
+      p->smem = SmemBytes<7>(stages); break;
+    case 8: p->fn = gosa ? (const void *)HimenoKernel<8, true> : (const void *)HimenoKernel<8, false>;
+      p->smem = SmemBytes<8>(stages); break;
+    case 11: p->fn = gosa ? (const void *)HimenoKernel<11, true> : (const void *)HimenoKernel<11, false>;
+      p->smem = SmemBytes<11>(stages); break;
+    default: p->fn = gosa ? (const void *)HimenoKernel<15, true> : (const void *)HimenoKernel<15, false>;
+      p->smem = SmemBytes<15>(stages); break;
+  }
   p->block = (TY + 1) * 32;
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+  PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared));
   int occ = 0;
   PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->fn, p->block, p->smem));
   PSB_CHECK(occ > 0, "himeno kernel does not fit on an SM");
+  if (rt->opt.himeno_occ > 0) occ = std::min(occ, rt->opt.himeno_occ);
 
   HimenoArgs &a = p->args;
   const float **coef[] = {&a.a0, &a.a1, &a.a2, &a.a3, &a.b0, &a.b1, &a.b2, &a.c0, &a.c1, &a.c2,

@@ -349,6 +349,8 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "star7_sthint") o->star7_sthint = (int)val;
   else if (k == "himeno_by") o->himeno_by = (int)val;
   else if (k == "himeno_zc") o->himeno_zc = (int)val;
+  else if (k == "himeno_stages") o->himeno_stages = (int)val;
+  else if (k == "himeno_occ") o->himeno_occ = (int)val;
   else if (k == "time_kernels") o->time_kernels = (int)val;
   else if (k == "stage_chunk_mb") o->stage_chunk = (size_t)val << 20;
   else return -1;

@@ -341,16 +341,24 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   Star7Plan *p = new Star7Plan();
   p->is_double = dbl;
   const Options &o = rt->opt;
+  // Tile shape: measured on B200 at 512^3 fp32 (tools/tune_star7.py, profiles/):
+  // two 512-byte boxes side by side x 16 rows, 2 rows per thread, 6-deep ring, one
+  // CTA per SM reaches 5.47 TB/s; rows narrower than two boxes use the one-box
+  // 8-row shape at 4 CTAs per SM.
   int variant = o.star7_variant;
-  if (variant < 0 || variant >= kNumVariants) variant = 0;
+  const size_t row_bytes = (size_t)(dom.local_max[0] - dom.local_min[0]) * (dbl ? 8 : 4);
+  const bool autov = variant < 0 || variant >= kNumVariants;
+  if (autov) variant = row_bytes >= 1024 ? 4 : 10;
   const VariantInfo &v = kVariants[variant];
   p->variant = variant;
   p->fn = dbl ? v.f64 : v.f32;
-  int stages = o.star7_stages > 0 ? std::min(o.star7_stages, kMaxStages) : 4;
+  int stages = o.star7_stages > 0 ? std::min(o.star7_stages, kMaxStages) : (variant == 4 ? 6 : 5);
   if (stages < 3) stages = 3;
   p->smem = dbl ? SmemBytes<double>(v, stages) : SmemBytes<float>(v, stages);
   p->block = (v.nbx * (v.ty / v.ry) + 1) * 32;
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+  PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared));
   int occ = 0;
   PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->fn, p->block, p->smem));
   PSB_CHECK(occ > 0, "star7 kernel does not fit on an SM");
@@ -367,9 +375,12 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
     // fewest z chunks (least z-halo re-reads) that still give every resident
     // CTA slot at least ~2 items, chunk count chosen so items divide the slots
     // as evenly as possible
+    // short chunks keep the statically strided items balanced across CTAs (the
+    // two extra halo planes per chunk mostly hit in L2); 32 planes measured best
+    // at 512^3, shrink further only when there would be fewer than ~4 items per slot
     int tiles = ntx * nty;
-    int want_chunks = std::max(1, CeilDiv(2L * slots, tiles));
-    zc = std::max(8, CeilDiv(nzd, want_chunks));
+    int want_chunks = std::max(1, CeilDiv(4L * slots, tiles));
+    zc = std::min(32, std::max(8, CeilDiv(nzd, want_chunks)));
     zc = std::min(zc, nzd);
   }
   const int nzc = CeilDiv(nzd, zc);

@@ -1,0 +1,124 @@
+"""CPU: the drop-in boundary.  The C-ABI library loads without a GPU, exports every symbol
+include/physis/physis_b200.h declares, its structs have the layout the ctypes mirror (and
+therefore generated code) assumes, and the product path fails loudly without a CUDA device."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+import helpers as H
+
+HEADER = os.path.join(H.ROOT, "include", "physis", "physis_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set()
+    for m in re.finditer(r"^[A-Za-z_][\w \*]*?\b(\w+)\s*\([^;{]*\)\s*;", src, flags=re.M):
+        line = m.group(0)
+        if "typedef" in line or "static" in line:
+            continue
+        names.add(m.group(1))
+    return names
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import physis_b200
+    from physis_b200 import api
+    lib = physis_b200.load_runtime()
+    declared = _declared_functions()
+    assert {"PSInit", "PSFinalize", "__PSGridNew", "__PSGridCopyin", "__PSGridCopyout",
+            "__PSReduceGridFloat", "__PSB200StencilRun", "PSDomain3DNew"} <= declared
+    for name in sorted(declared | set(api.EXPORTED_SYMBOLS)):
+        assert hasattr(lib, name), f"{name} declared in physis_b200.h but not exported"
+    assert set(api.EXPORTED_SYMBOLS) - {"__ps_trace"} <= declared
+
+
+def test_programs_library_exports_reference_benchmark_entry_points():
+    import physis_b200
+    lib = physis_b200.load_programs()
+    for name in ["initialize_physis", "initialize_benchmark_physis", "run_kernel_physis",
+                 "finalize_benchmark_physis", "himeno_init", "himeno_jacobi", "himeno_jacobi_gosa",
+                 "pstag_init", "pstag_run"]:
+        assert hasattr(lib, name)
+
+
+def test_struct_layouts_match_ctypes_mirror():
+    from physis_b200 import api
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "physis/physis_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(__PSDomain), sizeof(__PSGridTypeMemberInfo),
+         sizeof(__PSGridTypeInfo), sizeof(__PSGrid), sizeof(__PSB200StencilDesc), sizeof(__PSB200Stats));
+  printf("%zu %zu %zu %zu\n", offsetof(__PSGrid, dim), offsetof(__PSGrid, num_elms),
+         offsetof(__PSGrid, dev), offsetof(__PSB200StencilDesc, scalars));
+  printf("%zu %zu %zu\n", offsetof(__PSB200StencilDesc, grids), offsetof(__PSB200StencilDesc, launch),
+         offsetof(__PSB200StencilDesc, name));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "layout.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(td, "layout")
+        subprocess.check_call(["gcc", "-std=gnu11", "-I", os.path.join(H.ROOT, "include"), src, "-o", exe])
+        out = subprocess.check_output([exe], text=True).split()
+    got = [int(x) for x in out]
+    want = [C.sizeof(api.PSDomain), C.sizeof(api.MemberInfo), C.sizeof(api.TypeInfo),
+            C.sizeof(api.PSGridStruct), C.sizeof(api.StencilDesc), C.sizeof(api.Stats),
+            api.PSGridStruct.dim.offset, api.PSGridStruct.num_elms.offset, api.PSGridStruct.dev.offset,
+            api.StencilDesc.scalars.offset, api.StencilDesc.grids.offset, api.StencilDesc.launch.offset,
+            api.StencilDesc.name.offset]
+    assert got == want
+
+
+def test_header_is_plain_c_and_cxx():
+    with tempfile.TemporaryDirectory() as td:
+        for ext, cc in (("c", "gcc"), ("cc", "g++")):
+            src = os.path.join(td, "inc." + ext)
+            open(src, "w").write('#define PHYSIS_B200\n#include "physis/physis.h"\nint main(void){return 0;}\n')
+            subprocess.check_call([cc, "-fsyntax-only", "-Wall", "-I", os.path.join(H.ROOT, "include"), src])
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a machine without a CUDA device")
+def test_product_path_fails_loudly_without_gpu():
+    code = ("import sys; sys.path.insert(0, %r); from physis_b200 import api; api.PSInit()" % H.ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def test_missing_library_raises(monkeypatch, tmp_path):
+    import physis_b200._lib as L
+    monkeypatch.setattr(L, "_RT", None)
+    monkeypatch.setattr(L, "lib_dir", lambda: str(tmp_path))
+    with pytest.raises(L.NativeLibraryMissing):
+        L.load_runtime()
+
+
+def test_product_sources_do_not_touch_the_oracle():
+    bad = []
+    for base in ("physis_b200", "include", os.path.join("examples", "b200")):
+        for dp, _, files in os.walk(os.path.join(H.ROOT, base)):
+            for fn in files:
+                if fn.endswith((".so", ".o", ".pyc")):
+                    continue
+                text = open(os.path.join(dp, fn), errors="ignore").read()
+                if re.search(r"oracle[/_.]|liboracle|/root/reference/.*\.(so|a)\b", text) and "ORACLE" not in text:
+                    if re.search(r"(import|include|CDLL|dlopen|open)\W.*oracle", text):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad
