@@ -80,18 +80,20 @@ __global__ void __PSStencilRun_step_qp(__PSDomain dom, int zchunk, __PSGrid3DCel
   __PSB200_FOREACH_POINT_END
 }
 
-static void __PSStencilLaunch_step_pq(const void *sv, __PSB200Stream stream) {
+static void __PSStencilLaunch_step_pq(const void *sv, const __PSDomain *dom,
+        __PSB200Stream stream) {
   const struct __PSStencil_step_pq *s = (const struct __PSStencil_step_pq *)sv;
-  __PSB200GenericShape sh = __PSB200GenericShapeFor(&s->dom, 3);
+  __PSB200GenericShape sh = __PSB200GenericShapeFor(dom, 3);
   __PSStencilRun_step_pq<<<sh.grid, sh.block, 0, (cudaStream_t)stream>>>(
-      s->dom, sh.zchunk, *((__PSGrid3DCell_dev *)(s->u->dev)),
+      *dom, sh.zchunk, *((__PSGrid3DCell_dev *)(s->u->dev)),
       *((__PSGrid3DDouble_dev *)(s->kap->dev)));
 }
-static void __PSStencilLaunch_step_qp(const void *sv, __PSB200Stream stream) {
+static void __PSStencilLaunch_step_qp(const void *sv, const __PSDomain *dom,
+        __PSB200Stream stream) {
   const struct __PSStencil_step_qp *s = (const struct __PSStencil_step_qp *)sv;
-  __PSB200GenericShape sh = __PSB200GenericShapeFor(&s->dom, 3);
+  __PSB200GenericShape sh = __PSB200GenericShapeFor(dom, 3);
   __PSStencilRun_step_qp<<<sh.grid, sh.block, 0, (cudaStream_t)stream>>>(
-      s->dom, sh.zchunk, *((__PSGrid3DCell_dev *)(s->u->dev)),
+      *dom, sh.zchunk, *((__PSGrid3DCell_dev *)(s->u->dev)),
       *((__PSGrid3DDouble_dev *)(s->kap->dev)));
 }
 

@@ -99,11 +99,12 @@ __global__ void __PSStencilRun_kernel_physis(__PSDomain dom, int zchunk,
   __PSB200_FOREACH_POINT_END
 }
 
-static void __PSStencilLaunch_kernel_physis(const void *sv, __PSB200Stream stream) {
+static void __PSStencilLaunch_kernel_physis(const void *sv, const __PSDomain *dom,
+        __PSB200Stream stream) {
   const struct __PSStencil_kernel_physis *s = (const struct __PSStencil_kernel_physis *)sv;
-  __PSB200GenericShape sh = __PSB200GenericShapeFor(&s->dom, 3);
+  __PSB200GenericShape sh = __PSB200GenericShapeFor(dom, 3);
   __PSStencilRun_kernel_physis<<<sh.grid, sh.block, 0, (cudaStream_t)stream>>>(
-      s->dom, sh.zchunk, *((__PSGrid3DFloat_dev *)(s->g1->dev)),
+      *dom, sh.zchunk, *((__PSGrid3DFloat_dev *)(s->g1->dev)),
       *((__PSGrid3DFloat_dev *)(s->g2->dev)), s->ce, s->cw, s->cn, s->cs, s->ct, s->cb, s->cc);
 }
 

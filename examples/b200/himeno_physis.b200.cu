@@ -118,18 +118,19 @@ __global__ void __PSStencilRun_jacobi_kernel(__PSDomain dom, int zchunk,
   __PSB200_FOREACH_POINT_END
 }
 
-static void __PSStencilLaunch_jacobi_kernel(const void *sv, __PSB200Stream stream) {
+static void __PSStencilLaunch_jacobi_kernel(const void *sv, const __PSDomain *dom,
+        __PSB200Stream stream) {
   const struct __PSStencil_jacobi_kernel *s = (const struct __PSStencil_jacobi_kernel *)sv;
-  __PSB200GenericShape sh = __PSB200GenericShapeFor(&s->dom, 3);
+  __PSB200GenericShape sh = __PSB200GenericShapeFor(dom, 3);
   __PSJacobiDevArgs v;
   for (int i = 0; i < 15; ++i)
     v.g[i] = *((__PSGrid3DFloat_dev *)((s->g[i] ? s->g[i] : s->g[0])->dev));
   if (s->with_gosa)
     __PSStencilRun_jacobi_kernel<true><<<sh.grid, sh.block, 0, (cudaStream_t)stream>>>(
-        s->dom, sh.zchunk, v, s->omega);
+        *dom, sh.zchunk, v, s->omega);
   else
     __PSStencilRun_jacobi_kernel<false><<<sh.grid, sh.block, 0, (cudaStream_t)stream>>>(
-        s->dom, sh.zchunk, v, s->omega);
+        *dom, sh.zchunk, v, s->omega);
 }
 
 static void __PSStencilDescribe_jacobi_kernel(const struct __PSStencil_jacobi_kernel *s,

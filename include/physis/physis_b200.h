@@ -258,7 +258,12 @@ enum __PSB200Kind {
 
 /* cudaStream_t without dragging cuda_runtime.h into C translation units */
 typedef void *__PSB200Stream;
-typedef void (*__PSB200LaunchFunc)(const void *stencil, __PSB200Stream stream);
+/* Launch stub of a GENERIC sweep: enqueue one sweep of `stencil` over `dom` on
+ * `stream`.  `dom` is the stencil's own domain on one GPU; in a multi-GPU run the
+ * runtime passes the part of it this rank owns (global coordinates; the device
+ * views index globally).  Role of __PSDomainSetLocalSize, mpi_runtime_builder.cc:247-282. */
+typedef void (*__PSB200LaunchFunc)(const void *stencil, const __PSDomain *dom,
+                                   __PSB200Stream stream);
 
 typedef struct {
   int kind;                          /* enum __PSB200Kind */
@@ -272,6 +277,8 @@ typedef struct {
   const void *stencil;               /* GENERIC: the translated __PSStencil_<k> struct */
   __PSB200LaunchFunc launch;         /* GENERIC: enqueues one sweep on `stream` */
   const char *name;                  /* kernel name for --physis-trace */
+  unsigned written_mask;             /* GENERIC: bit i set = grids[i] is PSGridEmit'ed (multi-GPU
+                                      * halo refresh); 0 = unknown, refresh every grid */
 } __PSB200StencilDesc;
 
 /* for (i < iter) { sweep descs[0]; sweep descs[1]; ... } enqueued in order on
@@ -301,6 +308,23 @@ void __PSB200ResetStats(void);
 /* Runtime knobs (tile shape etc.) for tuning runs: "key=value". Returns 0 on success. */
 int __PSB200SetOption(const char *key_value);
 const char *__PSB200Version(void);
+/* ---- multi-GPU (one process per GPU, SPMD) ------------ */
+/* Rank / size of the process group PSInit joined (RANK, WORLD_SIZE, LOCAL_RANK,
+ * MASTER_PORT from the launcher's environment; 0 / 1 when launched alone). */
+int __PSB200Rank(void);
+int __PSB200WorldSize(void);
+/* The z-slab of a grid this rank owns (cf. __PSGetLocalOffset / __PSGetLocalSize,
+ * include/physis/physis_mpi_cuda.h:412-500). */
+void __PSB200GridLocalSize(void *g, int *z_offset, int *z_length);
+/* Slab-local transfers: the host buffer holds exactly this rank's z_length planes
+ * (PSGridCopyin/Copyout take and return the whole global array on every rank). */
+void __PSB200GridCopyinLocal(void *g, const void *src_slab);
+void __PSB200GridCopyoutLocal(void *g, void *dst_slab);
+/* Pure host helpers (no CUDA): the block decomposition and the shared-memory
+ * rendezvous, exposed so that they are testable on a CPU-only machine. */
+void __PSB200Partition(int n, int domain_n, int world, int rank, int *offset, int *length);
+int __PSB200GroupSelfTest(void);
+
 /* Page-locked host memory for callers that want DMA-speed Copyin/Copyout. */
 void *__PSB200HostAlloc(size_t bytes);
 void __PSB200HostFree(void *p);

@@ -45,7 +45,7 @@ class StencilDesc(C.Structure):
                 ("num_grids", C.c_int), ("grids", C.c_void_p * MAX_GRIDS),
                 ("members", C.c_int * MAX_GRIDS), ("num_scalars", C.c_int),
                 ("scalars", C.c_double * MAX_SCALARS), ("stencil", C.c_void_p),
-                ("launch", C.c_void_p), ("name", C.c_char_p)]
+                ("launch", C.c_void_p), ("name", C.c_char_p), ("written_mask", C.c_uint)]
 
 
 class Stats(C.Structure):
@@ -63,6 +63,8 @@ EXPORTED_SYMBOLS = [
     "__PSReduceGridLong", "__PSB200StencilRun", "__PSB200GetStream", "__PSB200Synchronize",
     "__PSB200TimerStart", "__PSB200TimerStopMs", "__PSB200GetStats", "__PSB200ResetStats",
     "__PSB200SetOption", "__PSB200Version", "__PSB200HostAlloc", "__PSB200HostFree", "__ps_trace",
+    "__PSB200Rank", "__PSB200WorldSize", "__PSB200GridLocalSize", "__PSB200GridCopyinLocal",
+    "__PSB200GridCopyoutLocal", "__PSB200Partition", "__PSB200GroupSelfTest",
 ]
 
 _bound = False
@@ -162,7 +164,7 @@ class Grid:
         ti, self._keep = _type_info(ptype, members)
         self.elm_size = ti.size
         d = (C.c_int * 3)(*(list(self.dims) + [0] * (3 - len(self.dims))))
-        self.h = rt().__PSGridNew(C.byref(ti), len(self.dims), d, None)
+        self.h = getattr(rt(), "__PSGridNew")(C.byref(ti), len(self.dims), d, None)  # no name mangling
         if not self.h:
             raise MemoryError("__PSGridNew returned INVALID_GRID")
         self.num_elms = int(np.prod(self.dims))
@@ -191,7 +193,7 @@ class Grid:
 
     def set(self, index, value_bytes):
         buf = np.frombuffer(bytes(value_bytes), dtype=np.uint8).copy()
-        rt().__PSGridSet(self.ptr, C.c_void_p(buf.ctypes.data), *[C.c_int(i) for i in index])
+        getattr(rt(), "__PSGridSet")(self.ptr, C.c_void_p(buf.ctypes.data), *[C.c_int(i) for i in index])
 
     def free(self):
         if self.h:

@@ -110,12 +110,12 @@ void Launch(const Grid &g, char *aos, bool to_soa, cudaStream_t s) {
   tile_elems = tile_elems / 16 * 16;
   PSB_CHECK(tile_elems >= 16, "user-defined point type too large");
   size_t smem = (size_t)tile_elems * g.elm_size;
-  long ntiles = (g.num_elms + tile_elems - 1) / tile_elems;
+  long ntiles = (g.n_alloc + tile_elems - 1) / tile_elems;
   int blocks = (int)std::min<long>(ntiles, 148L * 6);
   if (to_soa)
-    TransposeKernel<true><<<blocks, kThreads, smem, s>>>(aos, tbl, (long)g.num_elms, tile_elems);
+    TransposeKernel<true><<<blocks, kThreads, smem, s>>>(aos, tbl, (long)g.n_alloc, tile_elems);
   else
-    TransposeKernel<false><<<blocks, kThreads, smem, s>>>(aos, tbl, (long)g.num_elms, tile_elems);
+    TransposeKernel<false><<<blocks, kThreads, smem, s>>>(aos, tbl, (long)g.n_alloc, tile_elems);
   PSB_CUDA(cudaGetLastError());
 }
 

@@ -45,6 +45,10 @@ struct HimenoArgs {
   int xbase;
   int ntx, nty, nzc, zc, nitems;
   int stages;
+  // z-slab view (multi-GPU): local planes of p1 that are also stored into the ring
+  // neighbours' halo planes through the CUDA-IPC mapping; -1 / nullptr on one GPU
+  int push_lo_z, push_hi_z;
+  float *push_lo, *push_hi;
 };
 
 __device__ __forceinline__ float4 LdStream(const float *p) {
@@ -232,15 +236,22 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
           SetElem(o, j, v);
           SetElem(q, j, MulRn(ss, ss));
         }
+        float *const push0 = (z == a.push_lo_z) ? a.push_lo : nullptr;
+        float *const push1 = (z == a.push_hi_z) ? a.push_hi : nullptr;
+        const size_t gp = (size_t)y * a.nx + x;  // offset inside one plane
         if (all_ok) {
           *reinterpret_cast<float4 *>(a.p1 + g) = o;
           if (GOSA) *reinterpret_cast<float4 *>(a.gosa + g) = q;
+          if (push0) *reinterpret_cast<float4 *>(push0 + gp) = o;
+          if (push1) *reinterpret_cast<float4 *>(push1 + gp) = o;
         } else {
 #pragma unroll
           for (int j = 0; j < VEC; ++j) {
             if (ok[j]) {
               a.p1[g + j] = Elem(o, j);
               if (GOSA) a.gosa[g + j] = Elem(q, j);
+              if (push0) push0[gp + j] = Elem(o, j);
+              if (push1) push1[gp + j] = Elem(o, j);
             }
           }
         }
@@ -272,6 +283,7 @@ struct HimenoPlan {
   CUtensorMap tmap;
   HimenoArgs args;
   const void *fn = nullptr;
+  bool pushes = false;  // the kernel itself delivers the halo planes of p1
 };
 
 HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string *why) {
@@ -283,10 +295,12 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
     g[i] = Grid::FromHandle(d.grids[i]);
     if (g[i]->num_dims != 3 || g[i]->type != PS_FLOAT) { *why = "3-D float grids only"; return nullptr; }
     for (int k = 0; k < 3; ++k)
-      if (g[i]->dim[k] != g[0]->dim[k]) { *why = "grids must have equal extents"; return nullptr; }
+      if (g[i]->dim[k] != g[0]->dim[k] || g[i]->ldim[k] != g[0]->ldim[k]) {
+        *why = "grids must have equal extents"; return nullptr;
+      }
   }
   if (g[0] == g[1]) { *why = "in-place sweep"; return nullptr; }
-  const int nx = g[0]->dim[0], ny = g[0]->dim[1], nz = g[0]->dim[2];
+  const int nx = g[0]->ldim[0], ny = g[0]->ldim[1], nz = g[0]->ldim[2];  // local allocation
   const __PSDomain &dom = d.dom;
   if (nx % 4 != 0) { *why = "x extent must be a multiple of 4"; return nullptr; }
   // every read p(x±1, y±1, z±1) must stay inside the grid
@@ -354,6 +368,12 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
   a.nitems = a.ntx * a.nty * a.nzc;
   a.stages = stages;
   p->grid = std::min(a.nitems, slots);
+  a.push_lo_z = a.push_hi_z = -1;
+  if (SlabPushTargets(rt, *g[1], 0, (void **)&a.push_lo, (void **)&a.push_hi, sizeof(float))) {
+    a.push_lo_z = g[1]->halo;
+    a.push_hi_z = g[1]->halo + g[1]->nz_loc - 1;
+    p->pushes = true;
+  }
 
   int dimv[3] = {nx, ny, nz};
   int boxv[3] = {Geom<float>::BW, TY + 2, 1};
@@ -371,5 +391,6 @@ void LaunchHimeno(Runtime *rt, HimenoPlan *p) {
 }
 
 void DestroyHimeno(HimenoPlan *p) { delete p; }
+bool HimenoPushes(const HimenoPlan *p) { return p->pushes; }
 
 }  // namespace physis_b200

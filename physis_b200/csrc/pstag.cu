@@ -43,6 +43,12 @@ struct PstagArgs {
   int dx0, dx1, dy0, dy1, dz0, dz1;
   int ntx, nty, nzc, zc, nitems;
   int stages;
+  // z-slab view (multi-GPU): with halo planes in place the z wrap is the ring
+  // exchange, not a modulo; the written member's boundary planes are also stored
+  // into the neighbours' halo planes through the CUDA-IPC mapping
+  int zwrap;
+  int push_lo_z, push_hi_z;
+  double *push_lo, *push_hi;
 };
 
 __host__ __device__ constexpr int Up128(int v) { return (v + 127) / 128 * 128; }
@@ -123,7 +129,7 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
         if (bx0 + G::TXB >= a.nx) tx_bytes += TY * 16;
       }
       for (int zz = zb - 1; zz <= ze; ++zz) {
-        const int z = (zz + a.nz) % a.nz;
+        const int z = a.zwrap ? (zz + a.nz) % a.nz : zz;
         tma::mbar_wait(&empty[stage], phase ^ 1u);
         tma::mbar_arrive_expect_tx(&full[stage], tx_bytes);
         unsigned char *dst = planes + stage * STAGE_BYTES;
@@ -225,6 +231,8 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
         for (int r = 0; r < RY; ++r) top[r] = *reinterpret_cast<const double2 *>(p + r * ROWB);
       }
       const unsigned char *cb = box + stage_c * STAGE_BYTES;
+      double *const push0 = (z == a.push_lo_z) ? a.push_lo : nullptr;
+      double *const push1 = (z == a.push_hi_z) ? a.push_hi : nullptr;
       const double2 north = *reinterpret_cast<const double2 *>(cb + north_off + col_off);
       const double2 south = *reinterpret_cast<const double2 *>(cb + south_off + col_off);
 #pragma unroll
@@ -269,6 +277,8 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
         if (x_ok && in_grid && y >= a.dy0 && y < a.dy1) {
           double2 *dst = reinterpret_cast<double2 *>(a.out + ((size_t)z * a.ny + y) * a.nx + x);
           *dst = o;
+          if (push0) *reinterpret_cast<double2 *>(push0 + (size_t)y * a.nx + x) = o;
+          if (push1) *reinterpret_cast<double2 *>(push1 + (size_t)y * a.nx + x) = o;
         }
       }
       release(stage_c);
@@ -298,6 +308,8 @@ struct PstagPlan {
   CUtensorMap map_main, map_row, map_col;
   PstagArgs args;
   const void *fn = nullptr;
+  bool pushes = false;
+  int wr_member = 0;
 };
 
 PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *why) {
@@ -314,7 +326,7 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   if (mr.type != PS_DOUBLE || mw.type != PS_DOUBLE || mr.count != 1 || mw.count != 1) {
     *why = "members must be scalar doubles"; return nullptr;
   }
-  const int nx = u->dim[0], ny = u->dim[1], nz = u->dim[2];
+  const int nx = u->ldim[0], ny = u->ldim[1], nz = u->ldim[2];  // local allocation
   for (int i = 0; i < 3; ++i)
     if (kap->dim[i] != u->dim[i] + 1) { *why = "kap must be one larger than u per dimension"; return nullptr; }
   const __PSDomain &dom = d.dom;
@@ -324,7 +336,7 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   if (ny % kTY != 0 || (dom.local_min[1] % kTY) != 0) { *why = "y extent must be a multiple of the tile height"; return nullptr; }
   if (nx < Geom<double>::HX || nz < 1) { *why = "grid too small"; return nullptr; }
   for (int i = 0; i < 3; ++i)
-    if (dom.local_min[i] < 0 || dom.local_max[i] > u->dim[i] || dom.local_max[i] <= dom.local_min[i]) {
+    if (dom.local_min[i] < 0 || dom.local_max[i] > u->ldim[i] || dom.local_max[i] <= dom.local_min[i]) {
       *why = "bad domain"; return nullptr;
     }
   if (dom.local_min[0] != 0) { *why = "domain must start at x = 0"; return nullptr; }
@@ -340,10 +352,11 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   PSB_CHECK(occ > 0, "pstag kernel does not fit on an SM");
 
   PstagArgs &a = p->args;
+  p->wr_member = wr;
   a.out = (double *)mw.dev;
   a.kap = (const double *)kap->members[0].dev;
   a.nx = nx; a.ny = ny; a.nz = nz;
-  a.kx = kap->dim[0]; a.ky = kap->dim[1];
+  a.kx = kap->ldim[0]; a.ky = kap->ldim[1];
   a.dx0 = dom.local_min[0]; a.dx1 = dom.local_max[0];
   a.dy0 = dom.local_min[1]; a.dy1 = dom.local_max[1];
   a.dz0 = dom.local_min[2]; a.dz1 = dom.local_max[2];
@@ -358,6 +371,18 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   a.nitems = tiles * a.nzc;
   a.stages = stages;
   p->grid = std::min(a.nitems, slots);
+  a.zwrap = u->decomposed ? 0 : 1;
+  if (u->decomposed && (kap->halo < 1 || u->halo < 1 || kap->z_off != u->z_off)) {
+    *why = "decomposed run needs one halo plane and matching z cuts of u and kap";
+    delete p;
+    return nullptr;
+  }
+  a.push_lo_z = a.push_hi_z = -1;
+  if (SlabPushTargets(rt, *u, wr, (void **)&a.push_lo, (void **)&a.push_hi, sizeof(double))) {
+    a.push_lo_z = u->halo;
+    a.push_hi_z = u->halo + u->nz_loc - 1;
+    p->pushes = true;
+  }
 
   int dimv[3] = {nx, ny, nz};
   int box_main[3] = {Geom<double>::BW, kTY, 1};
@@ -379,5 +404,6 @@ void LaunchPstag(Runtime *rt, PstagPlan *p) {
 }
 
 void DestroyPstag(PstagPlan *p) { delete p; }
+bool PstagPushes(const PstagPlan *p) { return p->pushes; }
 
 }  // namespace physis_b200

@@ -20,6 +20,8 @@
 // only (tests bound it; exactly-representable data is bit-identical).
 #include "runtime.h"
 
+#include <vector>
+
 #include <cfloat>
 #include <climits>
 
@@ -58,7 +60,7 @@ struct Op {
     if (OP == PS_SUM) return (T)0;
     return (T)1;
   }
-  __device__ static T apply(T x, T y) {
+  __host__ __device__ static T apply(T x, T y) {
     using U = typename Unsigned<T>::type;
     if (OP == PS_MAX) return (x > y) ? x : y;
     if (OP == PS_MIN) return (x < y) ? x : y;
@@ -98,6 +100,12 @@ ReduceStage1(const T *__restrict__ data, long n, T *__restrict__ partials) {
   using V = typename Vec16<T>::type;
   constexpr int N = Vec16<T>::N;
   T acc = Op<T, OP>::identity();
+  // scalar head up to the first 16-byte boundary (a slab's interior starts after its
+  // halo planes, which need not be a multiple of 16 bytes)
+  const long head = min((long)(((16 - (reinterpret_cast<uintptr_t>(data) & 15)) & 15) / sizeof(T)), n);
+  if (blockIdx.x == 0 && threadIdx.x < head) acc = Op<T, OP>::apply(acc, data[threadIdx.x]);
+  data += head;
+  n -= head;
   const long nvec = n / N;
   const V *vdata = reinterpret_cast<const V *>(data);
   const long stride = (long)gridDim.x * kThreads;
@@ -140,20 +148,32 @@ ReduceStage2(const T *__restrict__ partials, int n, T *__restrict__ out) {
 
 template <typename T, int OP>
 void Run(Runtime *rt, const Grid &g, void *out_host) {
-  const long n = (long)g.num_elms;
+  // this rank's interior planes are contiguous in the local allocation
+  const long n = (long)g.plane_elms * g.nz_loc;
+  const T *data = (const T *)g.members[0].dev + (size_t)g.halo * g.plane_elms;
   constexpr int N = Vec16<T>::N;
   long want = (n / N + (long)kThreads * 4 - 1) / ((long)kThreads * 4);
   int blocks = (int)std::max<long>(1, std::min<long>(want, (long)rt->sm_count * 8));
   DeviceBuffer &scr = rt->small_scratch(sizeof(T) * (size_t)(blocks + 1));
   T *partials = (T *)scr.get();
   T *result = partials + blocks;
-  ReduceStage1<T, OP><<<blocks, kThreads, 0, rt->stream>>>((const T *)g.members[0].dev, n, partials);
+  ReduceStage1<T, OP><<<blocks, kThreads, 0, rt->stream>>>(data, n, partials);
   ReduceStage2<T, OP><<<1, kThreads, 0, rt->stream>>>(partials, blocks, result);
   PSB_CUDA(cudaGetLastError());
   rt->stats.kernel_launches += 2;
   PSB_CUDA(cudaMemcpyAsync(out_host, result, sizeof(T), cudaMemcpyDeviceToHost, rt->stream));
   PSB_CUDA(cudaStreamSynchronize(rt->stream));
   rt->stats.d2h_bytes += sizeof(T);
+  if (g.decomposed) {
+    // cross-GPU combine: one scalar per rank, folded in rank order on every rank
+    // (the reference: MPI_Reduce of the per-rank scalar, grid_space_mpi_cuda.h:571-598)
+    const int W = rt->world();
+    std::vector<T> all(W);
+    rt->comm->AllGather(out_host, all.data(), sizeof(T));
+    T acc = all[0];
+    for (int r = 1; r < W; ++r) acc = Op<T, OP>::apply(acc, all[r]);
+    *(T *)out_host = acc;
+  }
 }
 
 template <typename T>

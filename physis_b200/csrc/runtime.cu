@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <string>
+#include <vector>
 
 FILE *__ps_trace = nullptr;
 
@@ -83,9 +84,9 @@ static int ScalarSize(PSType t) {
   }
 }
 
-Grid *GridSpace::Create(const __PSGridTypeInfo *ti, int num_dims, const int *dim,
-                        cudaStream_t stream) {
+Grid *GridSpace::Create(const __PSGridTypeInfo *ti, int num_dims, const int *dim, Runtime *rt) {
   PSB_CHECK(num_dims >= 1 && num_dims <= PS_MAX_DIM, "unsupported grid dimensionality");
+  cudaStream_t stream = rt->stream;
   Grid *g = new Grid();
   g->id = next_id_++;
   g->type = ti->type;
@@ -94,8 +95,28 @@ Grid *GridSpace::Create(const __PSGridTypeInfo *ti, int num_dims, const int *dim
   g->num_elms = 1;
   for (int i = 0; i < num_dims; ++i) {
     g->dim[i] = dim[i];
+    g->ldim[i] = dim[i];
     g->num_elms *= dim[i];
   }
+
+  // z-slab decomposition: 3-D grids are cut along the last dimension over the
+  // ranks (the reference's default 1-D decomposition, runtime/runtime_mpi.h:130-136);
+  // lower-dimensional grids are replicated on every rank.
+  const int last = num_dims - 1;
+  g->plane_elms = g->num_elms / (dim[last] > 0 ? dim[last] : 1);
+  g->nz_loc = dim[last];
+  if (rt->world() > 1 && num_dims == 3) {
+    g->decomposed = true;
+    g->halo = rt->opt.halo;
+    int lo_off;
+    PartitionGridZ(dim[last], rt->domain_dims[last], rt->world(), rt->rank(), &g->z_off, &g->nz_loc);
+    PartitionGridZ(dim[last], rt->domain_dims[last], rt->world(), rt->comm->lo(), &lo_off,
+                   &g->lo_nz_loc);
+    PSB_CHECK(g->nz_loc >= g->halo && g->lo_nz_loc >= g->halo,
+              "a z-slab is thinner than the halo: use fewer GPUs for this grid");
+    g->ldim[last] = g->nz_loc + 2 * g->halo;
+  }
+  g->n_alloc = g->plane_elms * g->ldim[last];
 
   if (ti->type == PS_USER) {
     PSB_CHECK(ti->num_members > 0 && ti->members, "user type without member info");
@@ -125,28 +146,48 @@ Grid *GridSpace::Create(const __PSGridTypeInfo *ti, int num_dims, const int *dim
     g->members.push_back(ml);
   }
 
+  bool oom = false;
   for (auto &ml : g->members) {
     DeviceBuffer *b = new DeviceBuffer();
-    size_t bytes = (size_t)ml.size * ml.count * (size_t)g->num_elms;
+    size_t bytes = (size_t)ml.size * ml.count * (size_t)g->n_alloc;
     if (!b->Allocate(bytes, stream)) {
       delete b;
-      for (auto *s : g->storage) delete s;
-      delete g;
-      return nullptr;  // INVALID_GRID on OOM, as libphysis_rt_cuda.cc:66
+      oom = true;
+      break;
     }
     ml.dev = b->get();
     g->storage.push_back(b);
   }
+  if (g->decomposed) {
+    // collective: every rank must learn of a failed allocation before handles are exchanged
+    int mine = oom ? 1 : 0;
+    std::vector<int> all(rt->world());
+    rt->comm->AllGather(&mine, all.data(), sizeof(int));
+    for (int v : all) oom = oom || v;
+  }
+  if (oom) {
+    for (auto *s : g->storage) delete s;
+    delete g;
+    return nullptr;  // INVALID_GRID on OOM, as libphysis_rt_cuda.cc:66
+  }
+  if (g->decomposed) {
+    PSB_CUDA(cudaStreamSynchronize(stream));  // zero fill done before a neighbour may write
+    for (auto &ml : g->members) rt->ExchangeIpc(ml.dev, &ml.peer_lo, &ml.peer_hi);
+  }
 
-  // by-value device view: int dim[nd] (padded to 8) + one pointer per member
+  // by-value device view: int dim[nd] (padded to 8) + one pointer per member.  The
+  // view is in GLOBAL coordinates: pointers are shifted so that global plane z_off
+  // lands on the first interior plane of the local allocation.
   size_t ptr_off = ((size_t)num_dims * sizeof(int) + 7) / 8 * 8;
   size_t view_bytes = ptr_off + sizeof(void *) * g->members.size();
   g->dev_view = calloc(1, view_bytes);
   for (int i = 0; i < num_dims; ++i) ((int *)g->dev_view)[i] = dim[i];
+  const int64_t shift = (int64_t)(g->z_off - g->halo) * g->plane_elms;
   for (size_t m = 0; m < g->members.size(); ++m)
-    ((void **)((char *)g->dev_view + ptr_off))[m] = g->members[m].dev;
+    ((void **)((char *)g->dev_view + ptr_off))[m] =
+        (char *)g->members[m].dev - shift * g->members[m].size;
 
-  g->handle.p = g->members[0].dev;
+  g->handle.p = ((void **)((char *)g->dev_view + ptr_off))[0];
   for (int i = 0; i < PS_MAX_DIM; ++i) g->handle.dim[i] = (i < num_dims) ? dim[i] : 0;
   g->handle.elm_size = g->elm_size;
   g->handle.num_dims = num_dims;
@@ -158,6 +199,13 @@ Grid *GridSpace::Create(const __PSGridTypeInfo *ti, int num_dims, const int *dim
 
 void GridSpace::Destroy(Grid *g) {
   grids_.erase(g->id);
+  if (g->decomposed) {
+    Runtime *rt = Runtime::Get();
+    for (auto &ml : g->members) {
+      rt->CloseIpc(ml.peer_lo);
+      if (ml.peer_hi != ml.peer_lo) rt->CloseIpc(ml.peer_hi);
+    }
+  }
   for (auto *s : g->storage) delete s;
   free(g->dev_view);
   delete g;
@@ -168,9 +216,11 @@ Grid *GridSpace::Find(int id) const {
   return it == grids_.end() ? nullptr : it->second;
 }
 
-GridSpace::~GridSpace() {
+void GridSpace::Clear() {
   while (!grids_.empty()) Destroy(grids_.begin()->second);
 }
+
+GridSpace::~GridSpace() { Clear(); }
 
 // ---------------------------------------------------------------- runtime
 
@@ -244,6 +294,7 @@ void Runtime::Create(int *argc, char ***argv) {
   for (int i = 0; i < 2; ++i)
     PSB_CUDA(cudaEventCreateWithFlags(&rt->pinned_free_[i], cudaEventDisableTiming));
   g_rt = rt;
+  rt->InitGroup();
 }
 
 Runtime::~Runtime() {
@@ -258,6 +309,10 @@ Runtime::~Runtime() {
 
 void Runtime::Destroy() {
   if (!g_rt) return;
+  if (g_rt->stream) cudaStreamSynchronize(g_rt->stream);
+  if (g_rt->comm && g_rt->world() > 1) g_rt->comm->Barrier();  // nobody still writes my halos
+  g_rt->gs.Clear();
+  g_rt->ShutdownGroup();
   delete g_rt;
   g_rt = nullptr;
 }
@@ -352,6 +407,10 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "himeno_stages") o->himeno_stages = (int)val;
   else if (k == "himeno_occ") o->himeno_occ = (int)val;
   else if (k == "time_kernels") o->time_kernels = (int)val;
+  else if (k == "halo") o->halo = (int)val;
+  else if (k == "halo_push") o->halo_push = (int)val;
+  else if (k == "sync_mode") o->sync_mode = (int)val;
+  else if (k == "copyout_gather") o->copyout_gather = (int)val;
   else if (k == "stage_chunk_mb") o->stage_chunk = (size_t)val << 20;
   else return -1;
   return 0;
@@ -366,8 +425,15 @@ using namespace physis_b200;
 extern "C" {
 
 void PSInit(int *argc, char ***argv, int grid_num_dims, ...) {
-  (void)grid_num_dims;  // max grid extents follow as varargs; not needed on one GPU
+  // the maximum grid extents follow as varargs (physis_common.h:78); they fix where
+  // the z cuts of the process group fall (runtime/runtime_mpi.h:64-85)
+  int dd[PS_MAX_DIM] = {0, 0, 0};
+  va_list vl;
+  va_start(vl, grid_num_dims);
+  for (int i = 0; i < grid_num_dims && i < PS_MAX_DIM; ++i) dd[i] = va_arg(vl, PSIndex);
+  va_end(vl);
   Runtime::Create(argc, argv);
+  for (int i = 0; i < PS_MAX_DIM; ++i) Runtime::Get()->domain_dims[i] = dd[i];
   if (const char *env = getenv("PHYSIS_B200_OPTIONS")) {
     std::string s(env);
     size_t pos = 0;
@@ -425,7 +491,7 @@ __PSGrid *__PSGridNew(__PSGridTypeInfo *type_info, int num_dims, PSVectorInt dim
     g->handle.dev = (__PSGrid_dev *)func(num_dims, dim);
     return &g->handle;
   }
-  Grid *g = rt->gs.Create(type_info, num_dims, dim, rt->stream);
+  Grid *g = rt->gs.Create(type_info, num_dims, dim, rt);
   if (!g) return INVALID_GRID;
   return &g->handle;
 }
@@ -435,12 +501,76 @@ void __PSGridFree(void *gv, __PSGrid_devFreeFunc func) {
   Runtime *rt = Runtime::Get();
   Grid *g = Grid::FromHandle(gv);
   PSB_CUDA(cudaStreamSynchronize(rt->stream));
+  if (g->decomposed) rt->comm->Barrier();  // neighbours are done writing this grid's halos
   if (g->external_dev) {
     if (func && g->handle.dev) func(g->handle.dev);
     delete g;
     return;
   }
   rt->gs.Destroy(g);
+}
+
+// Pieces of the GLOBAL host array a rank's local allocation mirrors: the interior
+// slab plus each halo plane (ring wrap at the ends of the dimension).
+struct SlabSeg {
+  int64_t host_plane;
+  int local_plane;
+  int nplanes;
+};
+static int SlabSegments(const Grid &g, SlabSeg *out) {
+  int n = 0;
+  out[n++] = {g.z_off, g.halo, g.nz_loc};
+  const int gnz = g.dim[g.num_dims - 1];
+  for (int h = 1; h <= g.halo; ++h) {
+    out[n++] = {((g.z_off - h) % gnz + gnz) % gnz, g.halo - h, 1};
+    out[n++] = {(g.z_off + g.nz_loc + h - 1) % gnz, g.halo + g.nz_loc + h - 1, 1};
+  }
+  return n;
+}
+
+// Uploads planes of host data (AoS for user types) into the local allocation.
+static void UploadPlanes(Runtime *rt, Grid *g, const SlabSeg *segs, int nseg, const char *src,
+                         bool src_is_global) {
+  const size_t plane_bytes = (size_t)g->plane_elms * g->elm_size;
+  char *dst_base;
+  DeviceBuffer *tmp = nullptr;
+  if (g->is_user_type()) {
+    tmp = &rt->scratch(g->alloc_bytes());
+    if (nseg < 1 + 2 * g->halo || !src_is_global) {
+      // partial update: start from the current contents
+      LaunchSoaToAos(*g, tmp->get(), rt->stream);
+      rt->stats.kernel_launches++;
+    }
+    dst_base = (char *)tmp->get();
+  } else {
+    dst_base = (char *)g->members[0].dev;
+  }
+  for (int i = 0; i < nseg; ++i) {
+    const SlabSeg &sg = segs[i];
+    rt->CopyToDevice(dst_base + (size_t)sg.local_plane * plane_bytes,
+                     src + (size_t)sg.host_plane * plane_bytes, (size_t)sg.nplanes * plane_bytes);
+  }
+  if (tmp) {
+    LaunchAosToSoa(*g, tmp->get(), rt->stream);
+    rt->stats.kernel_launches++;
+    PSB_CUDA(cudaStreamSynchronize(rt->stream));
+  }
+}
+
+// Downloads the interior slab into `dst + dst_plane * plane_bytes`.
+static void DownloadInterior(Runtime *rt, Grid *g, char *dst, int64_t dst_plane) {
+  const size_t plane_bytes = (size_t)g->plane_elms * g->elm_size;
+  const char *src_base;
+  if (g->is_user_type()) {
+    DeviceBuffer &tmp = rt->scratch(g->alloc_bytes());
+    LaunchSoaToAos(*g, tmp.get(), rt->stream);
+    rt->stats.kernel_launches++;
+    src_base = (const char *)tmp.get();
+  } else {
+    src_base = (const char *)g->members[0].dev;
+  }
+  rt->CopyToHost(dst + (size_t)dst_plane * plane_bytes, src_base + (size_t)g->halo * plane_bytes,
+                 (size_t)g->nz_loc * plane_bytes);
 }
 
 void __PSGridCopyin(void *gv, const void *src, __PSGrid_devCopyinFunc func) {
@@ -451,16 +581,20 @@ void __PSGridCopyin(void *gv, const void *src, __PSGrid_devCopyinFunc func) {
     return;
   }
   PSB_CHECK(!g->external_dev, "copyin of an externally allocated grid needs its helper");
-  if (!g->is_user_type()) {
-    rt->CopyToDevice(g->members[0].dev, src, g->bytes());
+  if (g->decomposed) {
+    // every rank holds the same global host array (SPMD): take this rank's slab and
+    // its halo planes straight from it -- no inter-GPU traffic.  The barrier makes
+    // sure no neighbour is still pushing halos of an earlier sweep into this grid.
+    PSB_CUDA(cudaStreamSynchronize(rt->stream));
+    rt->comm->Barrier();
+    SlabSeg segs[1 + 2 * 8];
+    PSB_CHECK(g->halo <= 8, "halo too wide");
+    const int n = SlabSegments(*g, segs);
+    UploadPlanes(rt, g, segs, n, (const char *)src, true);
     return;
   }
-  // user type: stage the AoS bytes on the device, transpose there
-  DeviceBuffer &tmp = rt->scratch(g->bytes());
-  rt->CopyToDevice(tmp.get(), src, g->bytes());
-  LaunchAosToSoa(*g, tmp.get(), rt->stream);
-  rt->stats.kernel_launches++;
-  PSB_CUDA(cudaStreamSynchronize(rt->stream));
+  SlabSeg whole = {0, 0, g->ldim[g->num_dims - 1]};
+  UploadPlanes(rt, g, &whole, 1, (const char *)src, true);
 }
 
 void __PSGridCopyout(void *gv, void *dst, __PSGrid_devCopyoutFunc func) {
@@ -471,15 +605,91 @@ void __PSGridCopyout(void *gv, void *dst, __PSGrid_devCopyoutFunc func) {
     return;
   }
   PSB_CHECK(!g->external_dev, "copyout of an externally allocated grid needs its helper");
-  if (!g->is_user_type()) {
-    rt->CopyToHost(dst, g->members[0].dev, g->bytes());
-    return;
+  DownloadInterior(rt, g, (char *)dst, g->z_off);
+  if (g->decomposed && rt->opt.copyout_gather) {
+    // the reference hands the whole grid to the (single) user process; SPMD: every
+    // rank receives every slab (host-side all-gather, not on the hot path; programs
+    // that scale use __PSB200GridCopyoutLocal)
+    const int W = rt->world();
+    const size_t plane_bytes = (size_t)g->plane_elms * g->elm_size;
+    std::vector<size_t> off(W), len(W);
+    for (int r = 0; r < W; ++r) {
+      int o, l;
+      PartitionGridZ(g->dim[g->num_dims - 1], rt->domain_dims[g->num_dims - 1], W, r, &o, &l);
+      off[r] = (size_t)o * plane_bytes;
+      len[r] = (size_t)l * plane_bytes;
+    }
+    rt->comm->AllGatherV(dst, off.data(), len.data());
   }
-  DeviceBuffer &tmp = rt->scratch(g->bytes());
-  LaunchSoaToAos(*g, tmp.get(), rt->stream);
-  rt->stats.kernel_launches++;
-  rt->CopyToHost(dst, tmp.get(), g->bytes());
 }
+
+// Slab-local transfers for programs that scale (each rank owns the host copy of its
+// own slab only): `buf` holds exactly __PSB200GridLocalSize planes.  Counterparts of
+// the reference's per-rank sub-grid copies (runtime/rpc_cuda.h:79-135).
+void __PSB200GridCopyinLocal(void *gv, const void *src) {
+  Runtime *rt = Runtime::Get();
+  Grid *g = Grid::FromHandle(gv);
+  PSB_CUDA(cudaStreamSynchronize(rt->stream));
+  if (g->decomposed) rt->comm->Barrier();
+  SlabSeg seg = {0, g->halo, g->nz_loc};
+  UploadPlanes(rt, g, &seg, 1, (const char *)src, false);
+  if (g->decomposed) {
+    rt->comm->Barrier();        // every interior is in place
+    rt->PushAllHalos(*g);
+    PSB_CUDA(cudaStreamSynchronize(rt->stream));
+    rt->comm->Barrier();        // every halo is in place
+  }
+}
+
+void __PSB200GridCopyoutLocal(void *gv, void *dst) {
+  Runtime *rt = Runtime::Get();
+  Grid *g = Grid::FromHandle(gv);
+  DownloadInterior(rt, g, (char *)dst, 0);
+}
+
+void __PSB200GridLocalSize(void *gv, int *z_offset, int *z_length) {
+  Grid *g = Grid::FromHandle(gv);
+  if (z_offset) *z_offset = g->z_off;
+  if (z_length) *z_length = g->nz_loc;
+}
+
+void __PSB200Partition(int n, int domain_n, int world, int rank, int *offset, int *length) {
+  PartitionGridZ(n, domain_n, world, rank, offset, length);
+}
+
+// Rendezvous + barrier + all-gather round trip without touching CUDA; returns 0 on
+// success.  Uses the same environment as PSInit.
+int __PSB200GroupSelfTest(void) {
+  Comm *c = Comm::Create();
+  const int W = c->world(), r = c->rank();
+  int bad = 0;
+  std::vector<int> all(W);
+  for (int round = 0; round < 3; ++round) {
+    int mine = r * 100 + round;
+    c->AllGather(&mine, all.data(), sizeof(int));
+    for (int i = 0; i < W; ++i) bad += (all[i] != i * 100 + round);
+    c->Barrier();
+  }
+  // larger than one slot
+  std::vector<unsigned char> big(Comm::kSlotBytes * 2 + 17, (unsigned char)(r + 1)), got(big.size() * W);
+  c->AllGather(big.data(), got.data(), big.size());
+  for (int i = 0; i < W; ++i)
+    for (size_t k = 0; k < big.size(); k += 997) bad += (got[i * big.size() + k] != (unsigned char)(i + 1));
+  // variable-length gather through the window
+  std::vector<size_t> off(W), len(W);
+  size_t total = 0;
+  for (int i = 0; i < W; ++i) { off[i] = total; len[i] = 1000 + 333 * i; total += len[i]; }
+  std::vector<unsigned char> buf(total, 0);
+  for (size_t k = 0; k < len[r]; ++k) buf[off[r] + k] = (unsigned char)(r * 7 + k % 5);
+  c->AllGatherV(buf.data(), off.data(), len.data());
+  for (int i = 0; i < W; ++i)
+    for (size_t k = 0; k < len[i]; ++k) bad += (buf[off[i] + k] != (unsigned char)(i * 7 + k % 5));
+  delete c;
+  return bad;
+}
+
+int __PSB200Rank(void) { return Runtime::Get()->rank(); }
+int __PSB200WorldSize(void) { return Runtime::Get()->world(); }
 
 void PSGridCopyin(void *g, const void *src) { __PSGridCopyin(g, src, nullptr); }
 void PSGridCopyout(void *g, void *dst) { __PSGridCopyout(g, dst, nullptr); }
@@ -491,19 +701,33 @@ void __PSGridSet(__PSGrid *gh, void *buf, ...) {
   Grid *g = Grid::FromHandle(gh);
   va_list vl;
   va_start(vl, buf);
-  int64_t offset = 0, base = 1;
-  for (int i = 0; i < g->num_dims; ++i) {
-    PSIndex idx = va_arg(vl, PSIndex);
-    offset += idx * base;
+  PSIndex idx[PS_MAX_DIM] = {0, 0, 0};
+  for (int i = 0; i < g->num_dims; ++i) idx[i] = va_arg(vl, PSIndex);
+  va_end(vl);
+  const int last = g->num_dims - 1;
+  int64_t in_plane = 0, base = 1;
+  for (int i = 0; i < last; ++i) {
+    in_plane += idx[i] * base;
     base *= g->dim[i];
   }
-  va_end(vl);
-  // one element; for user types scatter each member of the struct
-  for (auto &ml : g->members) {
-    for (int c = 0; c < ml.count; ++c) {
-      char *d = (char *)ml.dev + ((size_t)c * g->num_elms + offset) * ml.size;
-      const char *s = (const char *)buf + ml.aos_offset + (size_t)c * ml.size;
-      PSB_CUDA(cudaMemcpyAsync(d, s, ml.size, cudaMemcpyHostToDevice, rt->stream));
+  if (g->decomposed) {
+    PSB_CUDA(cudaStreamSynchronize(rt->stream));
+    rt->comm->Barrier();
+  }
+  // every local plane (interior or halo copy) that mirrors global plane idx[last]
+  const int gnz = g->dim[last];
+  for (int lp = 0; lp < g->ldim[last]; ++lp) {
+    const int zg = (((g->z_off - g->halo + lp) % gnz) + gnz) % gnz;
+    const bool is_halo = lp < g->halo || lp >= g->halo + g->nz_loc;
+    if (zg != idx[last] || (!g->decomposed && is_halo)) continue;
+    const int64_t offset = in_plane + (int64_t)lp * g->plane_elms;
+    // one element; for user types scatter each member of the struct
+    for (auto &ml : g->members) {
+      for (int c = 0; c < ml.count; ++c) {
+        char *d = (char *)ml.dev + ((size_t)c * g->n_alloc + offset) * ml.size;
+        const char *s = (const char *)buf + ml.aos_offset + (size_t)c * ml.size;
+        PSB_CUDA(cudaMemcpyAsync(d, s, ml.size, cudaMemcpyHostToDevice, rt->stream));
+      }
     }
   }
   PSB_CUDA(cudaStreamSynchronize(rt->stream));

@@ -20,6 +20,7 @@
 
 #include "physis/physis_b200.h"
 #include "common.h"
+#include "comm.h"
 
 namespace physis_b200 {
 
@@ -69,7 +70,11 @@ struct MemberLayout {
   int size = 0;          // bytes of one scalar of this member
   int count = 1;         // array members: product of dims
   int aos_offset = 0;    // byte offset inside the host struct
-  void *dev = nullptr;   // device array [count][num_elms] (SoA; arrays plane-major)
+  void *dev = nullptr;   // local device array [count][n_alloc] (SoA; arrays plane-major)
+  // multi-GPU: the ring neighbours' allocations of the same member, mapped into
+  // this process with CUDA IPC (nullptr on one GPU)
+  void *peer_lo = nullptr;
+  void *peer_hi = nullptr;
 };
 
 // One Physis grid.  `handle` is what the generated code holds (its address is
@@ -80,9 +85,19 @@ class Grid {
   int id = 0;
   PSType type = PS_FLOAT;
   int num_dims = 0;
-  int dim[PS_MAX_DIM] = {1, 1, 1};
-  int64_t num_elms = 0;
+  int dim[PS_MAX_DIM] = {1, 1, 1};   // GLOBAL extents (what PSGridDim reports)
+  int64_t num_elms = 0;              // global element count
   int elm_size = 0;
+  // z-slab decomposition over the process group (role of GridMPI's local_size /
+  // local_offset / halo, runtime/grid_mpi.h:20-276).  The local allocation holds the
+  // planes [z_off - halo, z_off + nz_loc + halo) of the last dimension, halo planes
+  // in place.  On one GPU: z_off = 0, nz_loc = dim[last], halo = 0, ldim == dim.
+  bool decomposed = false;
+  int ldim[PS_MAX_DIM] = {1, 1, 1};  // local allocated extents
+  int z_off = 0, nz_loc = 0, halo = 0;
+  int64_t plane_elms = 0;            // elements of one plane of the decomposed dimension
+  int64_t n_alloc = 0;               // local allocated elements
+  int lo_nz_loc = 0;                 // interior planes of the lower ring neighbour
   std::vector<MemberLayout> members;   // size 1 for primitive grids
   std::vector<DeviceBuffer *> storage; // one per member
   void *dev_view = nullptr;            // host copy of the by-value device view
@@ -90,15 +105,23 @@ class Grid {
 
   bool is_user_type() const { return type == PS_USER; }
   size_t bytes() const { return (size_t)elm_size * (size_t)num_elms; }
+  size_t alloc_bytes() const { return (size_t)elm_size * (size_t)n_alloc; }
+  // local plane index of global plane zg of the decomposed dimension, or -1 when
+  // this rank does not hold it as an interior plane
+  int LocalInterior(int zg) const {
+    return (zg >= z_off && zg < z_off + nz_loc) ? zg - z_off + halo : -1;
+  }
   static Grid *FromHandle(void *h) { return reinterpret_cast<Grid *>(h); }
 };
 
 // id -> grid registry (role of GridSpace, runtime/grid.h:73-119).
+class Runtime;
 class GridSpace {
  public:
   ~GridSpace();
-  Grid *Create(const __PSGridTypeInfo *ti, int num_dims, const int *dim, cudaStream_t stream);
+  Grid *Create(const __PSGridTypeInfo *ti, int num_dims, const int *dim, Runtime *rt);
   void Destroy(Grid *g);
+  void Clear();
   Grid *Find(int id) const;
   size_t live() const { return grids_.size(); }
 
@@ -114,6 +137,12 @@ struct Options {
   int himeno_by = 0, himeno_zc = 0, himeno_stages = 0, himeno_occ = 0;
   int time_kernels = 0;        // per-family CUDA-event timing (for bench roofline)
   size_t stage_chunk = 32u << 20;  // pinned staging chunk for pageable copies
+  // multi-GPU
+  int halo = 1;          // halo planes per side of decomposed grids
+  int halo_push = 1;     // 1: specialised sweeps store their boundary planes straight into
+                         //    the neighbour's halo (fused); 0: peer copies after the kernel
+  int sync_mode = 0;     // 0: stream memory operations, 1: signal/wait kernels
+  int copyout_gather = 1;  // PSGridCopyout fills the whole host array on every rank
 };
 
 class Runtime {
@@ -147,6 +176,30 @@ class Runtime {
 
   cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
 
+  // ---- process group (one process per GPU; see comm.h, multigpu.cu) ----
+  Comm *comm = nullptr;
+  int domain_dims[PS_MAX_DIM] = {0, 0, 0};  // PSInit's maximum grid extents
+  int world() const { return comm ? comm->world() : 1; }
+  int rank() const { return comm ? comm->rank() : 0; }
+  // neighbour-completion flags: flags[0] is written by the lower neighbour,
+  // flags[1] by the upper one, with the number of the sweep they finished
+  uint32_t *flags = nullptr;
+  uint32_t *flags_of_lo = nullptr;   // IPC mappings of the neighbours' flag words
+  uint32_t *flags_of_hi = nullptr;
+  uint32_t sweep_epoch = 0;          // sweeps enqueued so far (identical on every rank)
+  void InitGroup();
+  void ShutdownGroup();
+  // stream-ordered: wait until both neighbours have finished sweep `epoch`
+  void WaitNeighbours(uint32_t epoch);
+  // stream-ordered: tell both neighbours this rank has finished sweep `epoch`
+  void SignalNeighbours(uint32_t epoch);
+  // copies this rank's boundary planes of one member into the neighbours' halos
+  void PushHalos(Grid &g, int member);
+  void PushAllHalos(Grid &g);
+  // maps `mine` (a cudaMalloc base) into the neighbours; returns their pointers
+  void ExchangeIpc(void *mine, void **of_lo, void **of_hi);
+  void CloseIpc(void *peer);
+
  private:
   Runtime() = default;
   ~Runtime();
@@ -157,6 +210,13 @@ class Runtime {
 };
 
 // ---- kernels (defined in the .cu files) ---------------------------------
+
+// Where a fused sweep must store its first / last interior plane of (g, member) so
+// that it lands in the ring neighbours' halo planes: base pointers of those planes
+// in the peers' IPC-mapped allocations.  False when the exchange is not fused
+// (one GPU, halo wider than one plane, or opt.halo_push == 0).
+bool SlabPushTargets(Runtime *rt, const Grid &g, int member, void **to_lo, void **to_hi,
+                     size_t elem_size);
 
 // AoS (host struct order) <-> SoA (one array per member) on the device.
 void LaunchAosToSoa(const Grid &g, const void *aos_dev, cudaStream_t s);

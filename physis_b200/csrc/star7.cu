@@ -29,6 +29,7 @@
 #include "sweep_common.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace physis_b200 {
 
@@ -48,6 +49,13 @@ struct Star7Args {
   int stages;
   int l2_hint;   // 1: loads carry an evict_first policy
   int st_hint;   // 1: streaming (evict-first) stores
+  // z-slab view (multi-GPU; on one GPU zcl = {0, nz-1} and nothing is pushed):
+  // local planes at which the bottom / top neighbour is clamped to the centre,
+  int zcl_lo, zcl_hi;
+  // and the local planes whose result is also stored, through the CUDA-IPC peer
+  // mapping, into the ring neighbour's halo plane (fused halo exchange over NVLink)
+  int push_lo_z, push_hi_z;
+  T *push_lo, *push_hi;
 };
 
 template <typename T>
@@ -204,7 +212,9 @@ Star7Kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
       const unsigned char *cb = box + stage_c * STAGE_BYTES;
       const V north = *reinterpret_cast<const V *>(cb + row0 * ROWB + col_off);
       const V south = *reinterpret_cast<const V *>(cb + (row0 + RY + 1) * ROWB + col_off);
-      const bool z_first = (z == 0), z_last = (z == a.nz - 1);
+      const bool z_first = (z == a.zcl_lo), z_last = (z == a.zcl_hi);
+      T *const push0 = (z == a.push_lo_z) ? a.push_lo : nullptr;
+      T *const push1 = (z == a.push_hi_z) ? a.push_hi : nullptr;
 #pragma unroll
       for (int r = 0; r < RY; ++r) {
         const int y = ybase + r;
@@ -234,6 +244,8 @@ Star7Kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
         if (x_ok && y >= a.dy0 && y < a.dy1) {
           V *dst = reinterpret_cast<V *>(a.out + ((size_t)z * a.ny + y) * a.nx + x);
           StoreVec(dst, o, a.st_hint != 0);
+          if (push0) *reinterpret_cast<V *>(push0 + (size_t)y * a.nx + x) = o;
+          if (push1) *reinterpret_cast<V *>(push1 + (size_t)y * a.nx + x) = o;
         }
       }
       release(stage_c);
@@ -296,14 +308,19 @@ struct Star7Plan {
   Star7Args<float> af;
   Star7Args<double> ad;
   const void *fn = nullptr;
+  bool pushes = false;  // the kernel itself delivers the halo planes of `out`
 };
 
 template <typename T>
 static void FillArgs(Star7Args<T> *a, const __PSB200StencilDesc &d, const Grid *gin, Grid *gout) {
   a->out = (T *)gout->members[0].dev;
-  a->nx = gin->dim[0];
-  a->ny = gin->dim[1];
-  a->nz = gin->dim[2];
+  a->nx = gin->ldim[0];
+  a->ny = gin->ldim[1];
+  a->nz = gin->ldim[2];
+  a->zcl_lo = gin->LocalInterior(0);
+  a->zcl_hi = gin->LocalInterior(gin->dim[2] - 1);
+  a->push_lo_z = a->push_hi_z = -1;
+  a->push_lo = a->push_hi = nullptr;
   a->dx0 = d.dom.local_min[0]; a->dx1 = d.dom.local_max[0];
   a->dy0 = d.dom.local_min[1]; a->dy1 = d.dom.local_max[1];
   a->dz0 = d.dom.local_min[2]; a->dz1 = d.dom.local_max[2];
@@ -324,16 +341,16 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
     *why = "float or double grids of one type"; return nullptr;
   }
   for (int i = 0; i < 3; ++i)
-    if (gin->dim[i] != gout->dim[i]) { *why = "grids must have equal extents"; return nullptr; }
+    if (gin->dim[i] != gout->dim[i] || gin->ldim[i] != gout->ldim[i]) { *why = "grids must have equal extents"; return nullptr; }
   if (gin == gout) { *why = "in-place sweep"; return nullptr; }
   const bool dbl = gin->type == PS_DOUBLE;
   const int vec = dbl ? 2 : 4;
   const __PSDomain &dom = d.dom;
-  if (gin->dim[0] % vec != 0 || dom.local_min[0] % vec != 0 || dom.local_max[0] % vec != 0) {
+  if (gin->ldim[0] % vec != 0 || dom.local_min[0] % vec != 0 || dom.local_max[0] % vec != 0) {
     *why = "x extent and domain x-range must be multiples of 16 bytes"; return nullptr;
   }
   for (int i = 0; i < 3; ++i) {
-    if (dom.local_min[i] < 0 || dom.local_max[i] > gin->dim[i]) { *why = "domain exceeds grid"; return nullptr; }
+    if (dom.local_min[i] < 0 || dom.local_max[i] > gin->ldim[i]) { *why = "domain exceeds grid"; return nullptr; }
   }
   if (dom.local_max[0] <= dom.local_min[0] || dom.local_max[1] <= dom.local_min[1] ||
       dom.local_max[2] <= dom.local_min[2]) { *why = "empty domain"; return nullptr; }
@@ -387,7 +404,7 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   const int nitems = ntx * nty * nzc;
   p->grid = std::min(nitems, slots);
 
-  int dimv[3] = {gin->dim[0], gin->dim[1], gin->dim[2]};
+  int dimv[3] = {gin->ldim[0], gin->ldim[1], gin->ldim[2]};
   int boxv[3] = {dbl ? Geom<double>::BW : Geom<float>::BW, v.ty + 2, 1};
   if (!EncodeTensorMap3D(&p->tmap, dbl ? TmaElem::F64 : TmaElem::F32, gin->members[0].dev, dimv,
                          boxv)) {
@@ -401,6 +418,12 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
     a->stages = stages;
     a->l2_hint = o.star7_l2hint;
     a->st_hint = o.star7_sthint;
+    using ET = typename std::remove_pointer<decltype(a->out)>::type;
+    if (SlabPushTargets(rt, *gout, 0, (void **)&a->push_lo, (void **)&a->push_hi, sizeof(ET))) {
+      a->push_lo_z = gout->halo;
+      a->push_hi_z = gout->halo + gout->nz_loc - 1;
+      p->pushes = true;
+    }
   };
   if (dbl) { FillArgs(&p->ad, d, gin, gout); common(&p->ad); }
   else { FillArgs(&p->af, d, gin, gout); common(&p->af); }
@@ -415,5 +438,6 @@ void LaunchStar7(Runtime *rt, Star7Plan *p) {
 }
 
 void DestroyStar7(Star7Plan *p) { delete p; }
+bool Star7Pushes(const Star7Plan *p) { return p->pushes; }
 
 }  // namespace physis_b200

@@ -6,7 +6,9 @@
 // translator/reference_runtime_builder.cc:896-940).
 #include "runtime.h"
 
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace physis_b200 {
@@ -15,16 +17,19 @@ struct Star7Plan;
 Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *why);
 void LaunchStar7(Runtime *rt, Star7Plan *p);
 void DestroyStar7(Star7Plan *p);
+bool Star7Pushes(const Star7Plan *p);
 
 struct HimenoPlan;
 HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string *why);
 void LaunchHimeno(Runtime *rt, HimenoPlan *p);
 void DestroyHimeno(HimenoPlan *p);
+bool HimenoPushes(const HimenoPlan *p);
 
 struct PstagPlan;
 PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *why);
 void LaunchPstag(Runtime *rt, PstagPlan *p);
 void DestroyPstag(PstagPlan *p);
+bool PstagPushes(const PstagPlan *p);
 
 struct SweepPlan {
   int kind = 0;
@@ -34,7 +39,29 @@ struct SweepPlan {
   PstagPlan *pstag = nullptr;
   __PSB200LaunchFunc launch = nullptr;
   const void *stencil = nullptr;
+  __PSDomain dom;              // this rank's part of the domain
+  bool empty = false;          // ... which may be nothing
+  bool fused_push = false;     // the kernel stores the halo planes of what it writes
+  // (grid, member) pairs whose halo planes must reach the neighbours after the sweep
+  std::vector<std::pair<Grid *, int>> written;
 };
+
+// Clips the z-range of a domain to this rank's slab.  Specialised kernels work on
+// the local allocation (local plane indices); generic kernels index through the
+// shifted device view in global coordinates.
+static bool LocaliseDomain(const Grid *g, __PSDomain *dom, bool local_coords) {
+  if (!g->decomposed) return dom->local_max[2] > dom->local_min[2];
+  int lo = std::max(dom->local_min[2], g->z_off);
+  int hi = std::min(dom->local_max[2], g->z_off + g->nz_loc);
+  if (hi <= lo) {
+    dom->local_min[2] = dom->local_max[2] = 0;
+    return false;
+  }
+  const int shift = local_coords ? g->halo - g->z_off : 0;
+  dom->local_min[2] = lo + shift;
+  dom->local_max[2] = hi + shift;
+  return true;
+}
 
 static const char *KindName(int k) {
   switch (k) {
@@ -47,50 +74,121 @@ static const char *KindName(int k) {
   }
 }
 
-SweepPlan *PrepareSweep(Runtime *rt, const __PSB200StencilDesc &d) {
+SweepPlan *PrepareSweep(Runtime *rt, const __PSB200StencilDesc &d_in) {
   SweepPlan *p = new SweepPlan();
-  p->kind = d.kind;
-  p->name = d.name ? d.name : KindName(d.kind);
+  p->kind = d_in.kind;
+  p->name = d_in.name ? d_in.name : KindName(d_in.kind);
   std::string why;
-  switch (d.kind) {
-    case PSB200_KIND_DIFFUSION7_CLAMP:
-      p->star7 = PrepareStar7(rt, d, &why);
-      if (p->star7) return p;
-      break;
-    case PSB200_KIND_HIMENO19:
-    case PSB200_KIND_HIMENO19_GOSA:
-      p->himeno = PrepareHimeno(rt, d, &why);
-      if (p->himeno) return p;
-      break;
-    case PSB200_KIND_PERIODIC7_STAGGERED:
-      p->pstag = PreparePstag(rt, d, &why);
-      if (p->pstag) return p;
-      break;
-    case PSB200_KIND_GENERIC:
-      break;
-    default:
-      why = "unknown sweep kind";
+  Grid *g0 = d_in.num_grids > 0 ? Grid::FromHandle(d_in.grids[0]) : nullptr;
+  const bool multi = rt->world() > 1;
+  if (multi && d_in.kind != PSB200_KIND_GENERIC && g0) {
+    __PSB200StencilDesc d = d_in;
+    p->empty = !LocaliseDomain(g0, &d.dom, true);
+    p->dom = d.dom;
+    if (p->empty) {
+      // nothing of the domain lives here; the rank still takes part in the ordering
+      return p;
+    }
+    switch (d.kind) {
+      case PSB200_KIND_DIFFUSION7_CLAMP:
+        p->star7 = PrepareStar7(rt, d, &why);
+        if (p->star7) {
+          p->fused_push = Star7Pushes(p->star7);
+          p->written.push_back({Grid::FromHandle(d.grids[1]), 0});
+          return p;
+        }
+        break;
+      case PSB200_KIND_HIMENO19:
+      case PSB200_KIND_HIMENO19_GOSA:
+        p->himeno = PrepareHimeno(rt, d, &why);
+        if (p->himeno) {
+          p->fused_push = HimenoPushes(p->himeno);
+          p->written.push_back({Grid::FromHandle(d.grids[1]), 0});
+          return p;
+        }
+        break;
+      case PSB200_KIND_PERIODIC7_STAGGERED:
+        p->pstag = PreparePstag(rt, d, &why);
+        if (p->pstag) {
+          p->fused_push = PstagPushes(p->pstag);
+          p->written.push_back({Grid::FromHandle(d.grids[0]), d.members[1]});
+          return p;
+        }
+        break;
+      default:
+        why = "unknown sweep kind";
+    }
+  } else if (d_in.kind != PSB200_KIND_GENERIC) {
+    const __PSB200StencilDesc &d = d_in;
+    p->dom = d.dom;
+    switch (d.kind) {
+      case PSB200_KIND_DIFFUSION7_CLAMP:
+        p->star7 = PrepareStar7(rt, d, &why);
+        if (p->star7) return p;
+        break;
+      case PSB200_KIND_HIMENO19:
+      case PSB200_KIND_HIMENO19_GOSA:
+        p->himeno = PrepareHimeno(rt, d, &why);
+        if (p->himeno) return p;
+        break;
+      case PSB200_KIND_PERIODIC7_STAGGERED:
+        p->pstag = PreparePstag(rt, d, &why);
+        if (p->pstag) return p;
+        break;
+      default:
+        why = "unknown sweep kind";
+    }
   }
   // Shapes a specialised kernel does not cover run through the program's own
   // generic per-point kernel (still on the GPU); without one this is fatal.
-  if (d.launch) {
+  if (d_in.launch) {
     p->kind = PSB200_KIND_GENERIC;
-    p->launch = d.launch;
-    p->stencil = d.stencil;
+    p->launch = d_in.launch;
+    p->stencil = d_in.stencil;
+    p->dom = d_in.dom;
+    p->empty = false;
+    p->fused_push = false;
+    p->written.clear();
+    if (multi && g0) {
+      // the 3-D grid of the sweep that is decomposed decides the cut
+      const Grid *cut = nullptr;
+      for (int i = 0; i < d_in.num_grids && !cut; ++i)
+        if (Grid::FromHandle(d_in.grids[i])->decomposed) cut = Grid::FromHandle(d_in.grids[i]);
+      if (cut) p->empty = !LocaliseDomain(cut, &p->dom, false);
+      // which grids a generated kernel writes is only known to the translator
+      // (written_mask); without it every grid of the sweep is refreshed
+      for (int i = 0; i < d_in.num_grids; ++i) {
+        Grid *g = Grid::FromHandle(d_in.grids[i]);
+        if (!g->decomposed) continue;
+        if (d_in.written_mask && !(d_in.written_mask & (1u << i))) continue;
+        for (size_t m = 0; m < g->members.size(); ++m) p->written.push_back({g, (int)m});
+      }
+    }
     return p;
   }
   fprintf(stderr, "[physis-b200] sweep '%s' (%s) cannot run: %s, and the program carries no "
                   "generic launch stub. There is no CPU fallback.\n",
-          p->name.c_str(), KindName(d.kind), why.c_str());
+          p->name.c_str(), KindName(d_in.kind), why.c_str());
   exit(1);
 }
 
 void LaunchSweep(Runtime *rt, SweepPlan *p) {
-  if (p->star7) LaunchStar7(rt, p->star7);
-  else if (p->himeno) LaunchHimeno(rt, p->himeno);
-  else if (p->pstag) LaunchPstag(rt, p->pstag);
-  else p->launch(p->stencil, (__PSB200Stream)rt->stream);
-  rt->stats.kernel_launches++;
+  const bool multi = rt->world() > 1;
+  // neighbours must have finished the previous sweep: their halo stores into this
+  // rank are complete, and they no longer read the halo planes this sweep overwrites
+  if (multi) rt->WaitNeighbours(rt->sweep_epoch);
+  if (!p->empty) {
+    if (p->star7) LaunchStar7(rt, p->star7);
+    else if (p->himeno) LaunchHimeno(rt, p->himeno);
+    else if (p->pstag) LaunchPstag(rt, p->pstag);
+    else p->launch(p->stencil, &p->dom, (__PSB200Stream)rt->stream);
+    rt->stats.kernel_launches++;
+  }
+  if (multi) {
+    if (!p->fused_push)
+      for (auto &w : p->written) rt->PushHalos(*w.first, w.second);
+    rt->SignalNeighbours(++rt->sweep_epoch);
+  }
 }
 
 void DestroySweep(SweepPlan *p) {
@@ -108,6 +206,8 @@ using namespace physis_b200;
 
 extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200StencilDesc *descs) {
   Runtime *rt = Runtime::Get();
+  // every rank has finished its earlier (synchronous) runtime calls on the grids
+  if (rt->world() > 1) rt->comm->Barrier();
   std::vector<SweepPlan *> plans;
   plans.reserve(num_stencils);
   std::string names;

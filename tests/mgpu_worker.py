@@ -1,0 +1,99 @@
+"""One rank of a multi-GPU parity run (launched by tests/test_multigpu.py or by hand with
+torchrun-style environment).  Every rank runs the SAME Physis programs (SPMD) on global
+arrays, and compares what it gets back with the CPU oracle run on the same inputs."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers as H  # noqa: E402
+
+
+def check(name, want, got, view):
+    ok = np.array_equal(np.ascontiguousarray(want).view(view), np.ascontiguousarray(got).view(view))
+    if not ok:
+        w, g = np.ascontiguousarray(want).ravel(), np.ascontiguousarray(got).ravel()
+        bad = np.nonzero(w.view(view) != g.view(view))[0]
+        raise AssertionError(f"{name}: {bad.size} of {w.size} elements differ, first at {bad[:5]}: "
+                             f"want {w[bad[:3]]} got {g[bad[:3]]}")
+
+
+def case_diffusion():
+    for (nx, ny, nz), count in [((128, 32, 16), 6), ((64, 48, 37), 4), ((256, 16, 9), 2), ((30, 17, 11), 4)]:
+        rng = np.random.default_rng(nx + nz)
+        f0 = rng.random(nx * ny * nz, dtype=np.float32)
+        co = np.array([0.11, 0.07, 0.13, 0.05, 0.17, 0.03, 0.44], np.float32)
+        want = H.run_diffusion(H.oracle_port(), f0, nx, ny, nz, count, co)
+        got = H.run_diffusion(H.b200_programs(), f0, nx, ny, nz, count, co)
+        check(f"diffusion {nx}x{ny}x{nz}", want, got, np.uint32)
+        got = H.run_diffusion(H.b200_programs(), f0, nx, ny, nz, count, co, entry="run_kernel_physis_generic")
+        check(f"diffusion generic {nx}x{ny}x{nz}", want, got, np.uint32)
+
+
+def case_himeno():
+    for dims, nn in [((64, 32, 32), 4), ((128, 20, 13), 2)]:
+        a = H.run_himeno(H.oracle_port(), dims, nn, gosa=True, seed=5)
+        b = H.run_himeno(H.b200_programs(), dims, nn, gosa=True, seed=5)
+        check(f"himeno p0 {dims}", a[0], b[0], np.uint32)
+        check(f"himeno p1 {dims}", a[1], b[1], np.uint32)
+        check(f"himeno gosa grid {dims}", a[3], b[3], np.uint32)
+        exact = float(np.sum(a[3].astype(np.float64)))
+        assert abs(b[2] - exact) <= 8e-6 * abs(exact), (b[2], exact)
+
+
+def case_pstag():
+    for (nx, ny, nz), count in [((64, 16, 8), 4), ((128, 32, 11), 3)]:
+        u, kap = H.pstag_inputs(nx, ny, nz)
+        want = H.run_pstag(H.oracle_port(), u, kap, nx, ny, nz, count)
+        got = H.run_pstag(H.b200_programs(), u, kap, nx, ny, nz, count)
+        check(f"pstag {nx}x{ny}x{nz}", want, got, np.uint64)
+
+
+def case_api():
+    """Runtime calls through the ctypes mirror: slab-local copies, PSReduce, PSGridSet."""
+    from physis_b200 import api
+    rank = int(os.environ.get("RANK", "0"))
+    api.PSInit(["t"], 3, (32, 8, 21))
+    r = api.rt()
+    world = r.__PSB200WorldSize()
+    assert r.__PSB200Rank() == rank
+    g = api.Grid((32, 8, 21), api.PS_INT)
+    full = (np.arange(32 * 8 * 21, dtype=np.int64) % 1000 - 300).astype(np.int32)
+    g.copyin(full)
+    assert int(g.reduce(api.PS_SUM)) == int(full.sum())
+    assert int(g.reduce(api.PS_MAX)) == int(full.max())
+    assert int(g.reduce(api.PS_MIN)) == int(full.min())
+    back = g.copyout()
+    check("copyout gather", full, back, np.uint32)
+    off, ln = C.c_int(), C.c_int()
+    r.__PSB200GridLocalSize(g.ptr, C.byref(off), C.byref(ln))
+    plane = 32 * 8
+    mine = (full[off.value * plane:(off.value + ln.value) * plane] * 2).astype(np.int32)
+    r.__PSB200GridCopyinLocal(g.ptr, C.c_void_p(mine.ctypes.data))
+    assert int(g.reduce(api.PS_SUM)) == 2 * int(full.sum())
+    out = np.zeros_like(mine)
+    r.__PSB200GridCopyoutLocal(g.ptr, C.c_void_p(out.ctypes.data))
+    check("local round trip", mine, out, np.uint32)
+    g.set((3, 2, 20), np.int32(77777).tobytes())
+    g.set((1, 1, 0), np.int32(-5).tobytes())
+    back = g.copyout()
+    want = (full * 2).astype(np.int32)
+    want[3 + 2 * 32 + 20 * plane] = 77777
+    want[1 + 1 * 32] = -5
+    check("set", want, back, np.uint32)
+    g.free()
+    api.PSFinalize()
+    assert world == int(os.environ.get("WORLD_SIZE", "1"))
+
+
+CASES = {"diffusion": case_diffusion, "himeno": case_himeno, "pstag": case_pstag, "api": case_api}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        CASES[n]()
+    print("ok rank", os.environ.get("RANK", "0"), names, flush=True)
