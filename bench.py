@@ -235,35 +235,43 @@ def run_b200(args, rank, world, dist):
     from physis_b200 import api
     import helpers as H
 
-    if world > 1:
-        raise SystemExit("multi-GPU bench path not wired yet in this revision")
-
     lib = physis_b200.load_programs()
     n, count = args.size, args.count
-    npts = n ** 3
-    # synthetic initial field of the benchmark's shape (smooth cosine product)
-    ax = (1.0 - np.cos(2 * np.pi * (np.arange(n, dtype=np.float64) + 0.5) / n)).astype(np.float32)
-    f0 = (0.125 * ax[:, None, None] * ax[None, :, None] * ax[None, None, :]).astype(np.float32).ravel()
+    # weak scaling: n^3 points per GPU, the global grid is n x n x (n*world) cut into z-slabs
+    # (strong scaling: --strong keeps the global grid at n^3)
+    gnz = n if args.strong else n * world
     co = [0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.4]
 
     lib.initialize_physis.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
-    lib.initialize_physis(0, None, n, n, n)
+    lib.initialize_physis(0, None, n, n, gnz)
     for kv in args.opt:
         api.set_option(kv)
-    lib.initialize_benchmark_physis(n, n, n)
-    lib.copyin_physis.argtypes = [C.c_void_p]
-    lib.copyout_physis.argtypes = [C.c_void_p]
+    lib.initialize_benchmark_physis(n, n, gnz)
+    lib.copyin_local_physis.argtypes = [C.c_void_p]
+    lib.copyout_local_physis.argtypes = [C.c_void_p]
     lib.run_sweeps_only_physis.argtypes = [C.c_int] * 4 + [C.c_float] * 7
-    lib.run_kernel_physis.argtypes = [C.c_int, C.c_void_p] + [C.c_int] * 3 + [C.c_float] * 7
+    lib.run_kernel_local_physis.argtypes = [C.c_int, C.c_void_p] + [C.c_int] * 3 + [C.c_float] * 7
     r = api.rt()
+    zo, zl = C.c_int(), C.c_int()
+    lib.local_size_physis(C.byref(zo), C.byref(zl))
+    z_off, nz_loc = zo.value, zl.value
+    npts_loc = n * n * nz_loc
+    npts_glob = n * n * gnz
 
-    host, host_ptr = api.pinned_empty(npts * 4, np.float32)
+    # synthetic initial field of the benchmark's shape (smooth cosine product), this rank's slab
+    def axis(m, lo=0, cnt=None):
+        i = np.arange(lo, lo + (m if cnt is None else cnt), dtype=np.float64)
+        return (1.0 - np.cos(2 * np.pi * (i + 0.5) / m)).astype(np.float32)
+    ax, az = axis(n), axis(gnz, z_off, nz_loc)
+    f0 = (0.125 * az[:, None, None] * ax[None, :, None] * ax[None, None, :]).astype(np.float32).ravel()
+
+    host, host_ptr = api.pinned_empty(npts_loc * 4, np.float32)
     host[:] = f0
-    lib.copyin_physis(host.ctypes.data)
+    lib.copyin_local_physis(host.ctypes.data)
 
     # ---- value: device-resident sweeps --------------------------------------
     for _ in range(args.warmup):
-        lib.run_sweeps_only_physis(count, n, n, n, *co)
+        lib.run_sweeps_only_physis(count, n, n, gnz, *co)
     r.__PSB200Synchronize()
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()
@@ -271,38 +279,38 @@ def run_b200(args, rank, world, dist):
     r.__PSB200ResetStats()
     r.__PSB200TimerStart()
     for _ in range(args.steps):
-        lib.run_sweeps_only_physis(count, n, n, n, *co)
+        lib.run_sweeps_only_physis(count, n, n, gnz, *co)
     ms = r.__PSB200TimerStopMs()
     _barrier(dist)
     st = api.stats()
     launches = int(st.kernel_launches)
     ms = _max_over_ranks(dist, ms)
     clocks = sampler.stop()
-    value = npts * count * args.steps * world / ms / 1e6  # GLUP/s
+    value = npts_glob * count * args.steps / ms / 1e6  # GLUP/s, all ranks
 
     # ---- e2e: copyin (pinned host) + sweeps + copyout per step --------------
     for _ in range(min(args.warmup, 2)):
-        lib.run_kernel_physis(count, host.ctypes.data, n, n, n, *co)
+        lib.run_kernel_local_physis(count, host.ctypes.data, n, n, gnz, *co)
     host[:] = f0
     _barrier(dist)
     r.__PSB200TimerStart()
     for _ in range(args.steps):
-        lib.run_kernel_physis(count, host.ctypes.data, n, n, n, *co)
+        lib.run_kernel_local_physis(count, host.ctypes.data, n, n, gnz, *co)
     ms_e2e = r.__PSB200TimerStopMs()
     _barrier(dist)
     ms_e2e = _max_over_ranks(dist, ms_e2e)
-    e2e = npts * count * args.steps * world / ms_e2e / 1e6
+    e2e = npts_glob * count * args.steps / ms_e2e / 1e6
     checksum = float(np.sum(host[::4097], dtype=np.float64))
 
-    # ---- roofline of the dominant kernel --------------------------------------
+    # ---- roofline of the dominant kernel (per GPU) ------------------------------
     peak, peak_src = _peaks()
-    alg_bytes = 8 * npts                      # 1 fp32 read + 1 fp32 write per point per launch
-    launch_ms = ms / max(launches, 1)
+    alg_bytes = 8 * npts_loc                  # 1 fp32 read + 1 fp32 write per point per launch
+    launch_ms = ms / max(count * args.steps, 1)
     achieved = alg_bytes / launch_ms / 1e6     # GB/s
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": _traffic("Star7Kernel<float>"),
                 "kernel": "Star7Kernel<float>", "alg_bytes_per_launch": alg_bytes,
-                "launch_ms": launch_ms, "peak_source": peak_src}
+                "launch_ms": launch_ms, "peak_source": peak_src, "per": "GPU"}
 
     lib.finalize_benchmark_physis()
     r.__PSB200HostFree(C.c_void_p(host_ptr))
@@ -310,19 +318,23 @@ def run_b200(args, rank, world, dist):
     line = {
         "metric": "7-pt diffusion GLUP/s", "value": value, "unit": "GLUP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"7-pt 3D diffusion fp32 {n}^3 per GPU, {count} sweeps per step "
-                               "(BASELINE config 2)",
-                   "l2": f"working set {2 * npts * 4 / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
+        "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"7-pt 3D diffusion fp32 {n}x{n}x{gnz} over {world} GPU(s) "
+                               f"({n}x{n}x{nz_loc} z-slab per GPU), {count} sweeps per step "
+                               "(BASELINE config 2 per GPU)",
+                   "l2": f"working set {2 * npts_loc * 4 / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)",
+                   "parallelism": f"z-slabs x{world}, halo planes stored peer-to-peer by the sweep",
                    "options": args.opt},
-        "e2e": {"value": e2e, "unit": "GLUP/s", "h2d_bytes_per_step": npts * 4,
-                "d2h_bytes_per_step": npts * 4, "ms_per_step": ms_e2e / args.steps,
+        "e2e": {"value": e2e, "unit": "GLUP/s", "h2d_bytes_per_step": npts_loc * 4 * world,
+                "d2h_bytes_per_step": npts_loc * 4 * world, "ms_per_step": ms_e2e / args.steps,
                 "checksum": checksum},
         "gpu_launches": launches,
         "roofline": roofline,
         "clocks": clocks,
     }
+    if world > 1:
+        line["halo_bytes_per_step"] = int(2 * n * n * 4 * count)
     if rank == 0 and world == 1 and not args.no_himeno:
         line["himeno"] = himeno_line(args, api, lib)
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -344,6 +356,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--himeno", default="XL")
     ap.add_argument("--himeno-nn", type=int, default=20)
+    ap.add_argument("--strong", action="store_true", help="keep the global grid at size^3 (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -163,6 +163,19 @@ void run_sweeps_only_physis(int count, int nx, int ny, int nz,
                                                 ce, cw, cn, cs, ct, cb, cc));
 }
 void copyin_physis(const REAL *f1_host) { __PSGridCopyin(f1g, f1_host, NULL); }
+/* multi-GPU bench hooks: this rank's slab only (see __PSB200GridCopyinLocal) */
+void copyin_local_physis(const REAL *slab) { __PSB200GridCopyinLocal(f1g, slab); }
+void copyout_local_physis(REAL *slab) { __PSB200GridCopyoutLocal(f1g, slab); }
+void local_size_physis(int *z_off, int *z_len) { __PSB200GridLocalSize(f1g, z_off, z_len); }
+void run_kernel_local_physis(int count, REAL *slab, int nx, int ny, int nz,
+                             REAL ce, REAL cw, REAL cn, REAL cs, REAL ct, REAL cb, REAL cc) {
+  PSDomain3D dom = PSDomain3DNew(0, nx, 0, ny, 0, nz);
+  __PSB200GridCopyinLocal(f1g, slab);
+  __PSStencilRun_0(count/2,
+                   __PSStencilMap_kernel_physis(dom, f1g, f2g, ce, cw, cn, cs, ct, cb, cc),
+                   __PSStencilMap_kernel_physis(dom, f2g, f1g, ce, cw, cn, cs, ct, cb, cc));
+  __PSB200GridCopyoutLocal(f1g, slab);
+}
 void copyout_physis(REAL *f1_host) { __PSGridCopyout(f1g, f1_host, NULL); }
 
 /* same sweeps forced through the generic per-point kernel (tests / comparison) */
