@@ -317,8 +317,8 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
   // groups of four, so 7+1 (two CTAs per SM) and 15+1 fill the register file where
   // 8+1 strands three warps' worth.
   int TY = rt->opt.himeno_by;
-  if (TY != 7 && TY != 8 && TY != 11 && TY != 15) TY = 7;
-  int stages = rt->opt.himeno_stages > 0 ? std::min(rt->opt.himeno_stages, kMaxStages) : 5;
+  if (TY != 7 && TY != 8 && TY != 11 && TY != 15) TY = 15;  // measured best (profiles/r1_tune_himeno_XL.csv)
+  int stages = rt->opt.himeno_stages > 0 ? std::min(rt->opt.himeno_stages, kMaxStages) : 6;
   if (stages < 4) stages = 4;
   switch (TY) {
     case 7: p->fn = gosa ? (const void *)HimenoKernel<7, true> : (const void *)HimenoKernel<7, false>;
@@ -332,12 +332,21 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
   }
   p->block = (TY + 1) * 32;
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+  // The coefficient streams are ordinary global loads: the in-flight lines live in L1,
+  // so the shared-memory carve-out is only what the p ring needs and L1 keeps the rest.
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 cudaSharedmemCarveoutMaxShared));
   int occ = 0;
   PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->fn, p->block, p->smem));
   PSB_CHECK(occ > 0, "himeno kernel does not fit on an SM");
   if (rt->opt.himeno_occ > 0) occ = std::min(occ, rt->opt.himeno_occ);
+  {
+    const size_t need = (p->smem + 1024) * (size_t)occ;
+    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    pct = std::max(rt->opt.himeno_carveout > 0 ? rt->opt.himeno_carveout : pct, pct);
+    PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  std::min(pct, 100)));
+  }
 
   HimenoArgs &a = p->args;
   const float **coef[] = {&a.a0, &a.a1, &a.a2, &a.a3, &a.b0, &a.b1, &a.b2, &a.c0, &a.c1, &a.c2,
@@ -359,8 +368,8 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
   int zc = rt->opt.himeno_zc;
   if (zc <= 0) {
     int tiles = a.ntx * a.nty;
-    int want_chunks = std::max(1, CeilDiv(2L * slots, tiles));
-    zc = std::max(8, CeilDiv(nzd, want_chunks));
+    int want_chunks = std::max(1, CeilDiv(4L * slots, tiles));
+    zc = std::min(64, std::max(8, CeilDiv(nzd, want_chunks)));
     zc = std::min(zc, nzd);
   }
   a.zc = zc;

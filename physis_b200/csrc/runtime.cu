@@ -401,11 +401,13 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "star7_occ") o->star7_occ = (int)val;
   else if (k == "star7_variant") o->star7_variant = (int)val;
   else if (k == "star7_l2hint") o->star7_l2hint = (int)val;
+  else if (k == "star7_impl") o->star7_impl = (int)val;
   else if (k == "star7_sthint") o->star7_sthint = (int)val;
   else if (k == "himeno_by") o->himeno_by = (int)val;
   else if (k == "himeno_zc") o->himeno_zc = (int)val;
   else if (k == "himeno_stages") o->himeno_stages = (int)val;
   else if (k == "himeno_occ") o->himeno_occ = (int)val;
+  else if (k == "himeno_carveout") o->himeno_carveout = (int)val;
   else if (k == "time_kernels") o->time_kernels = (int)val;
   else if (k == "halo") o->halo = (int)val;
   else if (k == "halo_push") o->halo_push = (int)val;

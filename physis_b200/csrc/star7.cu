@@ -263,17 +263,313 @@ Star7Kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
   }
 }
 
+
+// ---------------------------------------------------------------- second form
+//
+// Same structure and results as Star7Kernel, with the consumers' instruction
+// count cut to what the stencil needs (ncu of the first form: 64 % of issue
+// slots busy, the fp32 work being a third of the instructions): clamps are taken
+// out of the per-element path (z: register copies on the one plane that needs
+// them; y: warp-uniform branch; x: one select on the edge lanes), the z window
+// rotates by renaming instead of moving registers, addresses advance by adds,
+// the mbarrier wait is two instructions on its fast path, and -- fp32 only --
+// the six additions per point run as packed add.rn.f32x2 (SASS FADD2) on pairs
+// of separately rounded scalar products.  (ptxas contracts a packed multiply
+// feeding a packed add into FFMA2 even with explicit .rn, which would change the
+// rounding, so the multiplies stay scalar.)
+
+namespace v2 {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 Pack(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void Unpack(u64 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 Add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// out vector from centre c, neighbours: west/east scalars of the vector's ends,
+// and the s, n, b, t vectors.  ((((((cc*c + cw*w) + ce*e) + cs*s) + cn*n) + cb*b) + ct*t)
+template <int FP>
+__device__ __forceinline__ float4 Vec7(const Star7Args<float> &a, float4 c, float wv, float ev,
+                                       float4 s, float4 n, float4 b, float4 t) {
+  float4 o;
+  if (FP == 0) {
+    o.x = Point7<float>(a, c.x, wv, c.y, s.x, n.x, b.x, t.x);
+    o.y = Point7<float>(a, c.y, c.x, c.z, s.y, n.y, b.y, t.y);
+    o.z = Point7<float>(a, c.z, c.y, c.w, s.z, n.z, b.z, t.z);
+    o.w = Point7<float>(a, c.w, c.z, ev, s.w, n.w, b.w, t.w);
+  } else {
+    // separately rounded products, then packed adds in the reference's order
+    u64 r01 = Pack(MulRn(a.cc, c.x), MulRn(a.cc, c.y));
+    u64 r23 = Pack(MulRn(a.cc, c.z), MulRn(a.cc, c.w));
+    r01 = Add2(r01, Pack(MulRn(a.cw, wv), MulRn(a.cw, c.x)));
+    r23 = Add2(r23, Pack(MulRn(a.cw, c.y), MulRn(a.cw, c.z)));
+    r01 = Add2(r01, Pack(MulRn(a.ce, c.y), MulRn(a.ce, c.z)));
+    r23 = Add2(r23, Pack(MulRn(a.ce, c.w), MulRn(a.ce, ev)));
+    r01 = Add2(r01, Pack(MulRn(a.cs, s.x), MulRn(a.cs, s.y)));
+    r23 = Add2(r23, Pack(MulRn(a.cs, s.z), MulRn(a.cs, s.w)));
+    r01 = Add2(r01, Pack(MulRn(a.cn, n.x), MulRn(a.cn, n.y)));
+    r23 = Add2(r23, Pack(MulRn(a.cn, n.z), MulRn(a.cn, n.w)));
+    r01 = Add2(r01, Pack(MulRn(a.cb, b.x), MulRn(a.cb, b.y)));
+    r23 = Add2(r23, Pack(MulRn(a.cb, b.z), MulRn(a.cb, b.w)));
+    r01 = Add2(r01, Pack(MulRn(a.ct, t.x), MulRn(a.ct, t.y)));
+    r23 = Add2(r23, Pack(MulRn(a.ct, t.z), MulRn(a.ct, t.w)));
+    Unpack(r01, o.x, o.y);
+    Unpack(r23, o.z, o.w);
+  }
+  return o;
+}
+template <int FP>
+__device__ __forceinline__ double2 Vec7(const Star7Args<double> &a, double2 c, double wv, double ev,
+                                        double2 s, double2 n, double2 b, double2 t) {
+  double2 o;
+  o.x = Point7<double>(a, c.x, wv, c.y, s.x, n.x, b.x, t.x);
+  o.y = Point7<double>(a, c.y, c.x, ev, s.y, n.y, b.y, t.y);
+  return o;
+}
+
+__device__ __forceinline__ float First(const float4 &v) { return v.x; }
+__device__ __forceinline__ float Last(const float4 &v) { return v.w; }
+__device__ __forceinline__ double First(const double2 &v) { return v.x; }
+__device__ __forceinline__ double Last(const double2 &v) { return v.y; }
+
+}  // namespace v2
+
+// FR ("full row"): the NBX boxes of a tile cover a whole grid row, so boxes carry no
+// x halo (the x neighbours of a box's edge lanes live in the adjacent box of the same
+// stage) and a tile's rows are contiguous in memory: no halo over-fetch in x, and
+// every plane of a tile is one contiguous DRAM range.
+template <typename T, int TY, int RY, int NBX, int MINB, int FP, bool FR>
+__global__ void __launch_bounds__((NBX * (TY / RY) + 1) * 32, MINB)
+Star7KernelV2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Star7Args<T> a) {
+  using G = Geom<T>;
+  using V = typename VecOf<T>::type;
+  constexpr int VEC = G::VEC;
+  constexpr int NWY = TY / RY;
+  constexpr int NW = NBX * NWY;  // consumer warps
+  constexpr int HXO = FR ? 0 : G::HX;                        // x halo elements per side
+  constexpr int ROWB = (G::TXB + 2 * HXO) * (int)sizeof(T);  // bytes of one box row
+  constexpr int BOX_STRIDE = ((TY + 2) * ROWB + 127) / 128 * 128;
+  constexpr int STAGE_BYTES = NBX * BOX_STRIDE;
+  // where the element left of lane 0's vector / right of lane 31's vector lives,
+  // relative to that lane's own position in the row
+  constexpr int WEST_OFF = FR ? -BOX_STRIDE + (G::TXB - 1) * (int)sizeof(T) : -(int)sizeof(T);
+  constexpr int EAST_OFF = FR ? BOX_STRIDE - 31 * VEC * (int)sizeof(T) : VEC * (int)sizeof(T);
+  static_assert(TY % RY == 0, "TY must be a multiple of RY");
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *empty = full + kMaxStages;
+  unsigned char *planes = smem + kBarrierBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = a.stages;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      tma::mbar_init(&full[s], 1);
+      tma::mbar_init(&empty[s], NW);
+    }
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int tiles_xy = a.ntx * a.nty;
+
+  if (warp == NW) {
+    // ------------------------------------------------------------ producer
+    if (lane != 0) return;
+    tma::prefetch_tensormap(&tmap);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      const int zci = item / tiles_xy;
+      const int txy = item - zci * tiles_xy;
+      const int ty = txy / a.ntx;
+      const int tx = txy - ty * a.ntx;
+      const int x0 = a.xbase + tx * (NBX * G::TXB);
+      const int y0 = a.dy0 + ty * TY;
+      const int zb = a.dz0 + zci * a.zc;
+      const int ze = min(zb + a.zc, a.dz1);
+      const int zfirst = zb > 0 ? zb - 1 : zb;
+      const int zlast = min(ze, a.nz - 1);
+      int nbox = 0;
+#pragma unroll
+      for (int b = 0; b < NBX; ++b) nbox += (x0 + b * G::TXB < a.nx) ? 1 : 0;
+      const uint32_t tx_bytes = (uint32_t)nbox * (uint32_t)((TY + 2) * ROWB);
+      for (int z = zfirst; z <= zlast; ++z) {
+        tma::mbar_wait(&empty[stage], phase ^ 1u);
+        tma::mbar_arrive_expect_tx(&full[stage], tx_bytes);
+        unsigned char *dst = planes + stage * STAGE_BYTES;
+#pragma unroll
+        for (int b = 0; b < NBX; ++b) {
+          const int bx0 = x0 + b * G::TXB;
+          if (bx0 < a.nx)
+            tma::load_3d(dst + b * BOX_STRIDE, &tmap, &full[stage], bx0 - HXO, y0 - 1, z);
+        }
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------- consumers
+  const int bx = warp % NBX;
+  const int wy = warp / NBX;
+  // this thread's first own row (smem row wy*RY + 1) and column inside a stage
+  const unsigned char *my = planes + bx * BOX_STRIDE + (wy * RY + 1) * ROWB +
+                            (HXO + lane * VEC) * (int)sizeof(T);
+  const bool lane_first = (lane == 0), lane_last = (lane == 31);
+  // FR: the outermost boxes have no neighbour box (their outer x neighbour is clamped)
+  const bool rd_west = lane_first && (!FR || bx > 0);
+  const bool rd_east = lane_last && (!FR || bx < NBX - 1);
+  const size_t plane_elems = (size_t)a.nx * a.ny;
+
+  int stage = 0;       // ring position of the next plane to consume
+  uint32_t phase = 0;
+
+#define S7_ADVANCE() do { if (++stage == S) { stage = 0; phase ^= 1u; } } while (0)
+#define S7_RELEASE(st) do { __syncwarp(); if (lane_first) tma::mbar_arrive(&empty[st]); } while (0)
+#define S7_LOAD(DST, st) do { \
+    const unsigned char *p__ = my + (st) * STAGE_BYTES; \
+    _Pragma("unroll") for (int r = 0; r < RY; ++r) DST[r] = *reinterpret_cast<const V *>(p__ + r * ROWB); \
+  } while (0)
+
+  for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+    const int zci = item / tiles_xy;
+    const int txy = item - zci * tiles_xy;
+    const int ty = txy / a.ntx;
+    const int tx = txy - ty * a.ntx;
+    const int x = a.xbase + tx * (NBX * G::TXB) + bx * G::TXB + lane * VEC;
+    const int ybase = a.dy0 + ty * TY + wy * RY;
+    const int zb = a.dz0 + zci * a.zc;
+    const int ze = min(zb + a.zc, a.dz1);
+    const bool x_ok = (x >= a.dx0) && (x + VEC <= a.dx1);
+    const bool x_first = (x == 0);
+    const bool x_last = (x + VEC == a.nx);
+    // rows whose y neighbour leaves the grid take the centre value instead
+    // (warp-uniform: every lane of a warp has the same rows)
+    const int r_north = -ybase;              // row with y == 0, if in [0, RY)
+    const int r_south = a.ny - 1 - ybase;    // row with y == ny-1, if in [0, RY)
+    const bool y_edge = (r_north >= 0 && r_north < RY) || (r_south >= 0 && r_south < RY);
+    bool st_ok[RY];
+    T *outp[RY];
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+      const int y = ybase + r;
+      st_ok[r] = x_ok && y >= a.dy0 && y < a.dy1;
+      outp[r] = a.out + ((size_t)zb * a.ny + y) * a.nx + x;
+    }
+
+    V w0[RY], w1[RY], w2[RY];  // the z window; roles rotate, registers do not move
+
+    if (zb > 0) {
+      tma::mbar_wait(&full[stage], phase);
+      S7_LOAD(w0, stage);
+      S7_RELEASE(stage);
+      S7_ADVANCE();
+    }
+    int stage_c = stage;
+    tma::mbar_wait(&full[stage], phase);
+    S7_LOAD(w1, stage);
+    S7_ADVANCE();
+    if (zb == a.zcl_lo || zb == 0) {
+      // bottom neighbour outside the grid: clamp to the centre
+#pragma unroll
+      for (int r = 0; r < RY; ++r) w0[r] = w1[r];
+    }
+
+    bool has_top = false;
+    int z = zb;
+
+    // one plane: BOT / CEN hold planes z-1 / z, TOP receives plane z+1
+#define S7_STEP(BOT, CEN, TOP) do { \
+      has_top = (z + 1 < a.nz); \
+      const int stage_t = stage; \
+      if (has_top) { tma::mbar_wait(&full[stage], phase); S7_LOAD(TOP, stage); } \
+      if (!has_top || z == a.zcl_hi) { \
+        _Pragma("unroll") for (int r = 0; r < RY; ++r) TOP[r] = CEN[r]; \
+      } \
+      const unsigned char *cb = my + stage_c * STAGE_BYTES; \
+      V north = *reinterpret_cast<const V *>(cb - ROWB); \
+      V south = *reinterpret_cast<const V *>(cb + RY * ROWB); \
+      T *const push0 = (z == a.push_lo_z) ? a.push_lo : nullptr; \
+      T *const push1 = (z == a.push_hi_z) ? a.push_hi : nullptr; \
+      _Pragma("unroll") for (int r = 0; r < RY; ++r) { \
+        const V c = CEN[r]; \
+        T wv = __shfl_up_sync(0xffffffffu, v2::Last(c), 1); \
+        T ev = __shfl_down_sync(0xffffffffu, v2::First(c), 1); \
+        if (rd_west) wv = *reinterpret_cast<const T *>(cb + r * ROWB + WEST_OFF); \
+        if (rd_east) ev = *reinterpret_cast<const T *>(cb + r * ROWB + EAST_OFF); \
+        if (x_first) wv = v2::First(c); \
+        if (x_last) ev = v2::Last(c); \
+        V nv = (r == 0) ? north : CEN[r > 0 ? r - 1 : 0]; \
+        V sv = (r == RY - 1) ? south : CEN[r < RY - 1 ? r + 1 : r]; \
+        if (y_edge) { \
+          if (r == r_north) nv = c; \
+          if (r == r_south) sv = c; \
+        } \
+        const V o = v2::Vec7<FP>(a, c, wv, ev, sv, nv, BOT[r], TOP[r]); \
+        if (st_ok[r]) { \
+          StoreVec(reinterpret_cast<V *>(outp[r]), o, a.st_hint != 0); \
+          if (push0) *reinterpret_cast<V *>(push0 + (size_t)(ybase + r) * a.nx + x) = o; \
+          if (push1) *reinterpret_cast<V *>(push1 + (size_t)(ybase + r) * a.nx + x) = o; \
+        } \
+        outp[r] += plane_elems; \
+      } \
+      S7_RELEASE(stage_c); \
+      if (has_top) { stage_c = stage_t; S7_ADVANCE(); } \
+      ++z; \
+    } while (0)
+
+    for (;;) {
+      S7_STEP(w0, w1, w2);
+      if (z >= ze) break;
+      S7_STEP(w1, w2, w0);
+      if (z >= ze) break;
+      S7_STEP(w2, w0, w1);
+      if (z >= ze) break;
+    }
+    if (has_top) S7_RELEASE(stage_c);  // plane ze was loaded as the top plane only
+  }
+#undef S7_STEP
+#undef S7_LOAD
+#undef S7_RELEASE
+#undef S7_ADVANCE
+}
+
 // ------------------------------------------------------------------ host side
 
 struct VariantInfo {
   int ty, ry, nbx;
   const void *f32;
   const void *f64;
+  const void *f32_v2[2];  // second form: scalar / packed-add arithmetic
+  const void *f64_v2;
+  bool full_row;          // second form only: boxes without x halo covering whole rows
 };
 
 #define VARIANT(TY, RY, NBX, MINB) \
   { TY, RY, NBX, (const void *)Star7Kernel<float, TY, RY, NBX, MINB>, \
-    (const void *)Star7Kernel<double, TY, RY, NBX, MINB> }
+    (const void *)Star7Kernel<double, TY, RY, NBX, MINB>, \
+    {(const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 0, false>, \
+     (const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 1, false>}, \
+    (const void *)Star7KernelV2<double, TY, RY, NBX, MINB, 0, false>, false }
+#define VARIANT_FR(TY, RY, NBX, MINB) \
+  { TY, RY, NBX, nullptr, nullptr, \
+    {(const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 0, true>, \
+     (const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 1, true>}, \
+    (const void *)Star7KernelV2<double, TY, RY, NBX, MINB, 0, true>, true }
 
 const VariantInfo kVariants[] = {
     VARIANT(32, 4, 1, 2),  // 0: default
@@ -288,12 +584,21 @@ const VariantInfo kVariants[] = {
     VARIANT(32, 2, 1, 1),  // 9
     VARIANT(8, 2, 1, 4),   // 10
     VARIANT(32, 8, 1, 2),  // 11
+    VARIANT_FR(8, 2, 4, 1),   // 12: full rows of 4 boxes (512 floats / 256 doubles)
+    VARIANT_FR(16, 4, 4, 1),  // 13
+    VARIANT_FR(16, 2, 2, 1),  // 14: full rows of 2 boxes
+    VARIANT_FR(8, 4, 8, 1),   // 15: full rows of 8 boxes (1024 floats)
+    VARIANT_FR(8, 2, 2, 2),   // 16
+    VARIANT_FR(16, 4, 8, 1),  // 17
+    VARIANT_FR(8, 1, 2, 1),   // 18
+    VARIANT_FR(8, 2, 1, 4),   // 19: one box
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 template <typename T>
 size_t SmemBytes(const VariantInfo &v, int stages) {
-  size_t box = ((size_t)(v.ty + 2) * Geom<T>::ROW_BYTES + 127) / 128 * 128;
+  const size_t rowb = v.full_row ? (size_t)Geom<T>::TXB * sizeof(T) : (size_t)Geom<T>::ROW_BYTES;
+  size_t box = ((size_t)(v.ty + 2) * rowb + 127) / 128 * 128;
   return kBarrierBytes + (size_t)stages * v.nbx * box;
 }
 
@@ -358,19 +663,42 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   Star7Plan *p = new Star7Plan();
   p->is_double = dbl;
   const Options &o = rt->opt;
-  // Tile shape: measured on B200 at 512^3 fp32 (tools/tune_star7.py, profiles/):
-  // two 512-byte boxes side by side x 16 rows, 2 rows per thread, 6-deep ring, one
-  // CTA per SM reaches 5.47 TB/s; rows narrower than two boxes use the one-box
-  // 8-row shape at 4 CTAs per SM.
+  // Tile shape (measured on B200, tools/tune_star7.py, profiles/r1_tune_star7_512.csv):
+  // whenever a row fits 8 boxes the tile spans whole rows (no x halo, every plane of a
+  // tile one contiguous DRAM range): 8 rows x 4 boxes, 2 rows per thread, 6-deep ring,
+  // one CTA per SM reaches 5.8 TB/s at 512^3 fp32.  Wider rows use two haloed boxes x 16 rows.
   int variant = o.star7_variant;
   const size_t row_bytes = (size_t)(dom.local_max[0] - dom.local_min[0]) * (dbl ? 8 : 4);
   const bool autov = variant < 0 || variant >= kNumVariants;
-  if (autov) variant = row_bytes >= 1024 ? 4 : 10;
+  if (autov) {
+    const int boxes = (int)((gin->ldim[0] * (size_t)(dbl ? 8 : 4) + 511) / 512);
+    if (o.star7_impl == 0 || dom.local_min[0] != 0 || boxes > 8) variant = row_bytes >= 1024 ? 4 : 10;
+    else if (boxes <= 1) variant = 19;
+    else if (boxes == 2) variant = 14;
+    else if (boxes <= 4) variant = 12;
+    else variant = 15;
+  }
+  const int txb0 = dbl ? Geom<double>::TXB : Geom<float>::TXB;
+  if (kVariants[variant].full_row) {
+    // needs the second form and a tile that spans the whole row
+    const bool fits = dom.local_min[0] == 0 && gin->ldim[0] <= kVariants[variant].nbx * txb0 &&
+                      o.star7_impl != 0;
+    if (!fits) {
+      if (!autov) { *why = "full-row tile shape does not span this grid's rows"; delete p; return nullptr; }
+      variant = row_bytes >= 1024 ? 4 : 10;
+    }
+  }
   const VariantInfo &v = kVariants[variant];
   p->variant = variant;
-  p->fn = dbl ? v.f64 : v.f32;
-  int stages = o.star7_stages > 0 ? std::min(o.star7_stages, kMaxStages) : (variant == 4 ? 6 : 5);
+  // star7_impl: 0 = first form, 1 = second form, 2 = second form with packed adds (fp32)
+  const int impl = o.star7_impl;
+  if (impl == 0) p->fn = dbl ? v.f64 : v.f32;
+  else p->fn = dbl ? v.f64_v2 : v.f32_v2[impl == 2 ? 1 : 0];
+  int stages = o.star7_stages > 0 ? std::min(o.star7_stages, kMaxStages) : (variant == 10 ? 5 : 6);
   if (stages < 3) stages = 3;
+  // deepest ring that fits the 227 KB of one SM
+  while (stages > 3 && (dbl ? SmemBytes<double>(v, stages) : SmemBytes<float>(v, stages)) > 227 * 1024)
+    --stages;
   p->smem = dbl ? SmemBytes<double>(v, stages) : SmemBytes<float>(v, stages);
   p->block = (v.nbx * (v.ty / v.ry) + 1) * 32;
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
@@ -405,7 +733,7 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   p->grid = std::min(nitems, slots);
 
   int dimv[3] = {gin->ldim[0], gin->ldim[1], gin->ldim[2]};
-  int boxv[3] = {dbl ? Geom<double>::BW : Geom<float>::BW, v.ty + 2, 1};
+  int boxv[3] = {v.full_row ? txb0 : (dbl ? Geom<double>::BW : Geom<float>::BW), v.ty + 2, 1};
   if (!EncodeTensorMap3D(&p->tmap, dbl ? TmaElem::F64 : TmaElem::F32, gin->members[0].dev, dimv,
                          boxv)) {
     *why = "grid shape violates a TMA constraint";

@@ -48,13 +48,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 }
 
 // try_wait suspends in hardware up to a time limit, so this loop is not a hot
-// spin.  A bounded number of retries turns a lost arrival into a trap instead
-// of hanging the GPU.
+// spin; its fast path is two instructions.  A bounded number of retries turns a
+// lost arrival into a trap instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t tries = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++tries > (1u << 26)) __trap();
-  }
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .u32 t;\n"
+      "mov.u32 t, 0;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "add.u32 t, t, 1;\n"
+      "setp.lt.u32 q, t, 0x4000000;\n"
+      "@q bra MBAR_WAIT;\n"
+      "trap;\n"
+      "MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
 }
 
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m) {

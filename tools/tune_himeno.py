@@ -13,7 +13,7 @@ from physis_b200 import api
 
 size = sys.argv[1] if len(sys.argv) > 1 else "XL"
 mi, mj, mk = {"XL": (1024, 512, 512), "L": (512, 256, 256)}[size]
-nn = 6
+nn = 10
 lib = physis_b200.load_programs()
 lib.himeno_init.argtypes = [C.c_int] * 3
 lib.himeno_init(mi, mj, mk)
@@ -21,7 +21,7 @@ lib.himeno_sweeps_only.argtypes = [C.c_int, C.c_int]
 r = api.rt()
 pts = (mi - 2) * (mj - 2) * (mk - 2)
 rows = []
-for by, st, zc, occ, gosa in itertools.product([7, 8, 11, 15], [4, 5, 6, 8], [0, 32, 64, 128], [0, 1], [0]):
+for by, st, zc, occ, gosa in itertools.product([7, 8, 11, 15], [4, 6, 8], [0, 32, 64], [0, 1], [0]):
     api.set_option(f"himeno_by={by}")
     api.set_option(f"himeno_stages={st}")
     api.set_option(f"himeno_zc={zc}")

@@ -28,13 +28,14 @@ co = [0.1] * 6 + [0.4]
 r = api.rt()
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 rows = []
-variants = range(12)
-stages = [3, 4, 5, 6]
-zcs = [0, 16, 32, 64, 128]
+variants = [int(v) for v in os.environ.get('TUNE_VARIANTS', ','.join(str(i) for i in range(20))).split(',')]
+stages = [4, 5, 6, 8]
+zcs = [16, 32, 64, 128]
 hints = [(0, 0), (1, 0), (0, 1), (1, 1)]
 
 
 def measure(v, s, zc, l2, st, occ=0):
+    api.set_option(f"star7_impl={os.environ.get('TUNE_IMPL', '2')}")
     api.set_option(f"star7_variant={v}")
     api.set_option(f"star7_stages={s}")
     api.set_option(f"star7_zc={zc}")
