@@ -201,33 +201,76 @@ def cpu_baseline_sample():
                       "(libphysis_rt_ref + translator-shaped sweep), 1 thread (REF codegen is sequential)"}
 
 
-def himeno_line(args, api, lib):
-    """Extra: Himeno XL (1024x512x512) with the residual emitted every sweep + PSReduce."""
+def himeno_line(args, api, lib, world, dist):
+    """Extra: Himeno XL (1024x512x512 per GPU, z-slabs) sweep-only and with the residual emitted
+    every sweep + PSReduce.  Weak scaling: the global grid is 1024 x 512 x (512*world)."""
     mi, mj, mk = (1024, 512, 512) if args.himeno == "XL" else (512, 256, 256)
-    lib.himeno_init.argtypes = [C.c_int] * 3
-    lib.himeno_init(mi, mj, mk)
+    gmk = mk * world
+    lib.himeno_init_local.argtypes = [C.c_int] * 3
+    lib.himeno_init_local(mi, mj, gmk)
     nn = args.himeno_nn
     lib.himeno_sweeps_only.argtypes = [C.c_int, C.c_int]
     lib.himeno_reduce_gosa.restype = C.c_float
     out = {}
-    pts = (mi - 2) * (mj - 2) * (mk - 2)
+    pts = (mi - 2) * (mj - 2) * (gmk - 2)
+    peak, _ = _peaks()
     for with_gosa in (0, 1):
         for _ in range(2):
             lib.himeno_sweeps_only(nn, with_gosa)
+        api.rt().__PSB200Synchronize()
+        _barrier(dist)
         api.rt().__PSB200TimerStart()
         lib.himeno_sweeps_only(nn, with_gosa)
         gosa = lib.himeno_reduce_gosa() if with_gosa else 0.0
         ms = api.rt().__PSB200TimerStopMs()
+        _barrier(dist)
+        ms = _max_over_ranks(dist, ms)
         bpl = 64 if with_gosa else 56
         key = "with_residual" if with_gosa else "sweep_only"
+        gbs = pts * nn * bpl / ms / 1e6
         out[key] = {"glups": pts * nn / ms / 1e6, "ms_per_sweep": ms / nn,
-                    "alg_bytes_per_lup": bpl, "gbs": pts * nn * bpl / ms / 1e6}
+                    "alg_bytes_per_lup": bpl, "gbs": gbs, "roofline_frac_per_gpu": gbs / world / peak}
         if with_gosa:
             out[key]["gosa"] = float(gosa)
     lib.himeno_finalize()
-    out["size"] = f"{mi}x{mj}x{mk}"
+    out["size"] = f"{mi}x{mj}x{gmk} over {world} GPU(s)"
     out["sweeps"] = nn
     return out
+
+
+def pstag_line(args, api, lib, world, dist):
+    """Extra: BASELINE config 5 -- fp64 periodic 7-pt on a user type {p,q} with a staggered
+    coefficient grid, 512^3 cells per GPU (weak scaling), device SoA: 24 B/LUP."""
+    n = args.pstag_size
+    gnz = n * world
+    lib.pstag_init.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.pstag_init(0, None, n, n, gnz)
+    uo, ul, ko, kl = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    lib.pstag_local_size(C.byref(uo), C.byref(ul), C.byref(ko), C.byref(kl))
+    rng = np.random.default_rng(7)
+    u = np.zeros((ul.value * n * n, 2), np.float64)
+    u[:, 0] = rng.random(ul.value * n * n)
+    kap = np.full(kl.value * (n + 1) * (n + 1), 0.05, np.float64)
+    lib.pstag_copyin_local.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pstag_copyin_local(u.ctypes.data, kap.ctypes.data)
+    lib.pstag_sweeps_only.argtypes = [C.c_int] * 4
+    count = args.pstag_count
+    for _ in range(2):
+        lib.pstag_sweeps_only(count, n, n, gnz)
+    api.rt().__PSB200Synchronize()
+    _barrier(dist)
+    api.rt().__PSB200TimerStart()
+    lib.pstag_sweeps_only(count, n, n, gnz)
+    ms = api.rt().__PSB200TimerStopMs()
+    _barrier(dist)
+    ms = _max_over_ranks(dist, ms)
+    lib.pstag_finalize()
+    pts = n * n * gnz
+    peak, _ = _peaks()
+    gbs = pts * count * 24 / ms / 1e6
+    return {"glups": pts * count / ms / 1e6, "ms_per_sweep": ms / count, "alg_bytes_per_lup": 24,
+            "gbs": gbs, "roofline_frac_per_gpu": gbs / world / peak,
+            "size": f"{n}x{n}x{gnz} cells over {world} GPU(s)", "sweeps": count, "dtype": "f64"}
 
 
 def run_b200(args, rank, world, dist):
@@ -335,8 +378,11 @@ def run_b200(args, rank, world, dist):
     }
     if world > 1:
         line["halo_bytes_per_step"] = int(2 * n * n * 4 * count)
-    if rank == 0 and world == 1 and not args.no_himeno:
-        line["himeno"] = himeno_line(args, api, lib)
+    if not args.no_himeno:
+        h = himeno_line(args, api, lib, world, dist)
+        ps = pstag_line(args, api, lib, world, dist)
+        line["himeno"] = h
+        line["periodic_staggered_fp64"] = ps
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample()
     if rank == 0:
@@ -356,6 +402,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--himeno", default="XL")
     ap.add_argument("--himeno-nn", type=int, default=20)
+    ap.add_argument("--pstag-size", type=int, default=512)
+    ap.add_argument("--pstag-count", type=int, default=100)
     ap.add_argument("--strong", action="store_true", help="keep the global grid at size^3 (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -164,6 +164,16 @@ void pstag_sweeps_only(int count, int nx, int ny, int nz) {
                    __PSStencilMap_step_qp(dom, u, kap));
 }
 void pstag_copyout(struct Cell *u_host) { __PSGridCopyout(u, u_host, NULL); }
+/* bench hooks for runs that scale: every rank owns the host copy of its own slab only */
+void pstag_local_size(int *u_off, int *u_len, int *k_off, int *k_len) {
+  __PSB200GridLocalSize(u, u_off, u_len);
+  __PSB200GridLocalSize(kap, k_off, k_len);
+}
+void pstag_copyin_local(const struct Cell *u_slab, const double *kap_slab) {
+  __PSB200GridCopyinLocal(u, u_slab);
+  __PSB200GridCopyinLocal(kap, kap_slab);
+}
+void pstag_copyout_local(struct Cell *u_slab) { __PSB200GridCopyoutLocal(u, u_slab); }
 
 void pstag_finalize(void) {
   __PSGridFree(u, NULL);

@@ -186,6 +186,33 @@ void himeno_init(int mimax, int mjmax, int mkmax) {
   free(host_buf);
 }
 
+/* bench hook for runs that scale: the same initial state, but every rank generates and
+ * uploads only its own z-slab (the program above builds the whole array on every rank) */
+void himeno_init_local(int mimax, int mjmax, int mkmax) {
+  int argc = 0;
+  char **argv = NULL;
+  PSInit(&argc, &argv, 3, mimax, mjmax, mkmax);
+  for (int g = 0; g < NGRIDS; ++g) G[g] = new_float3d(mimax, mjmax, mkmax);
+  int z_off = 0, z_len = 0;
+  __PSB200GridLocalSize(G[P0], &z_off, &z_len);
+  const size_t plane = (size_t)mimax * mjmax;
+  float *buf = (float *)malloc(plane * (size_t)z_len * sizeof(float));
+  for (int k = 0; k < z_len; ++k) {
+    const int kg = z_off + k;
+    const float v = (float)(kg * kg) / ((mkmax - 1) * (mkmax - 1));
+    for (size_t i = 0; i < plane; ++i) buf[(size_t)k * plane + i] = v;
+  }
+  __PSB200GridCopyinLocal(G[P0], buf);
+  __PSB200GridCopyinLocal(G[P1], buf);
+  const struct { int g; float v; } consts[] = {{BND, 1.0f}, {A0, 1.0f}, {A1, 1.0f}, {A2, 1.0f},
+      {A3, (float)(1.0 / 6.0)}, {B0, 0.0f}, {B1, 0.0f}, {B2, 0.0f}, {C0, 1.0f}, {C1, 1.0f}, {C2, 1.0f}};
+  for (size_t c = 0; c < sizeof(consts) / sizeof(consts[0]); ++c) {
+    for (size_t i = 0; i < plane * (size_t)z_len; ++i) buf[i] = consts[c].v;
+    __PSB200GridCopyinLocal(G[consts[c].g], buf);
+  }
+  free(buf);
+}
+
 void himeno_set_grid(int which, const float *buf) { __PSGridCopyin(G[which], buf, NULL); }
 void himeno_get_grid(int which, float *buf) { __PSGridCopyout(G[which], buf, NULL); }
 void himeno_set_omega(float w) { omega = w; }

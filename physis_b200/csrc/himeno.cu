@@ -369,7 +369,7 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
   if (zc <= 0) {
     int tiles = a.ntx * a.nty;
     int want_chunks = std::max(1, CeilDiv(4L * slots, tiles));
-    zc = std::min(64, std::max(8, CeilDiv(nzd, want_chunks)));
+    zc = std::min(32, std::max(8, CeilDiv(nzd, want_chunks)));
     zc = std::min(zc, nzd);
   }
   a.zc = zc;
