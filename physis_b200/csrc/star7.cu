@@ -665,18 +665,18 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   const Options &o = rt->opt;
   // Tile shape (measured on B200, tools/tune_star7.py, profiles/r1_tune_star7_512.csv):
   // whenever a row fits 8 boxes the tile spans whole rows (no x halo, every plane of a
-  // tile one contiguous DRAM range): 8 rows x 4 boxes, 2 rows per thread, 6-deep ring,
+  // tile one contiguous DRAM range) when a row fits 4 boxes: 8 rows x 4 boxes, 2 rows per thread, 6-deep ring,
   // one CTA per SM reaches 5.8 TB/s at 512^3 fp32.  Wider rows use two haloed boxes x 16 rows.
   int variant = o.star7_variant;
   const size_t row_bytes = (size_t)(dom.local_max[0] - dom.local_min[0]) * (dbl ? 8 : 4);
   const bool autov = variant < 0 || variant >= kNumVariants;
   if (autov) {
     const int boxes = (int)((gin->ldim[0] * (size_t)(dbl ? 8 : 4) + 511) / 512);
-    if (o.star7_impl == 0 || dom.local_min[0] != 0 || boxes > 8) variant = row_bytes >= 1024 ? 4 : 10;
+    // (wider full-row tiles would need 4 rows per thread, which spills at 96 registers)
+    if (o.star7_impl == 0 || dom.local_min[0] != 0 || boxes > 4) variant = row_bytes >= 1024 ? 4 : 10;
     else if (boxes <= 1) variant = 19;
     else if (boxes == 2) variant = 14;
-    else if (boxes <= 4) variant = 12;
-    else variant = 15;
+    else variant = 12;
   }
   const int txb0 = dbl ? Geom<double>::TXB : Geom<float>::TXB;
   if (kVariants[variant].full_row) {
