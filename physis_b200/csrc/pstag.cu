@@ -80,6 +80,8 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
   using L = PstagLayout<TY>;
   constexpr int BOX_STRIDE = L::STRIDE;
   constexpr int STAGE_BYTES = NBX * BOX_STRIDE;
+  constexpr int NT = NW * 32;   // consumer threads
+  constexpr int KD = 3;         // kap slots: plane z+1 in use, z+2 and z+3 in flight (z+3 reuses the slot of z)
 
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -154,6 +156,9 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
 
   const int bx = warp % NBX;
   const int wy = warp / NBX;
+  const int ctid = threadIdx.x;  // consumer thread index (the producer is the last warp)
+  const double *kap_ring = reinterpret_cast<const double *>(planes + S * STAGE_BYTES);
+  const uint32_t kap_smem = tma::smem_u32(kap_ring);
   const int col_off = (G::HX + lane * VEC) * (int)sizeof(double);
   const int row0 = wy * RY;  // first own row inside the MAIN region
   const int north_off = (wy == 0) ? L::NORTH : (row0 - 1) * ROWB;
@@ -189,18 +194,37 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
     // kap values at plane z (lo) and z+1 (hi): rows ybase .. ybase+RY, x .. x+2
     double klo[RY + 1][3], khi[RY + 1][3];
 
-    auto load_kap = [&](double (&k)[RY + 1][3], int z) {
+    // kap is staged through shared memory with cp.async, two planes ahead of its use,
+    // so its global-load latency is off the consumers' critical path (its row pitch,
+    // (nx+1)*8 bytes, rules out TMA and 16-byte accesses).  Every thread copies and
+    // reads back only its own 3 x (RY+1) values: [slot][row][element][thread], 8 bytes.
+    const int kz_max = ze;  // last kap plane this item reads
+    auto issue_kap = [&](int z) {
+      const int zc_ = min(z, kz_max);
+      const int slot = z % KD;
 #pragma unroll
       for (int r = 0; r <= RY; ++r) {
         const int y = min(ybase + r, a.ky - 1);
-        const double *row = a.kap + ((size_t)z * a.ky + y) * a.kx;
+        const double *row = a.kap + ((size_t)zc_ * a.ky + y) * a.kx;
         const int xx = min(x, a.kx - 2);
-        const double v0 = __ldg(row + xx), v1 = __ldg(row + xx + 1);
-        double v2 = __shfl_down_sync(0xffffffffu, v0, 1);
-        if (lane == 31 || x + VEC >= a.nx) v2 = __ldg(row + min(xx + 2, a.kx - 1));
-        k[r][0] = v0; k[r][1] = v1; k[r][2] = v2;
+        const uint32_t dst = kap_smem + (uint32_t)(((slot * (RY + 1) + r) * 3) * NT + ctid) * 8u;
+        tma::cp_async8(dst, row + xx);
+        tma::cp_async8(dst + NT * 8u, row + xx + 1);
+        tma::cp_async8(dst + 2u * NT * 8u, row + min(xx + 2, a.kx - 1));
+      }
+      tma::cp_async_commit();
+    };
+    auto load_kap = [&](double (&k)[RY + 1][3], int z) {
+      const int slot = z % KD;
+#pragma unroll
+      for (int r = 0; r <= RY; ++r) {
+        const double *src = kap_ring + (size_t)((slot * (RY + 1) + r) * 3) * NT + ctid;
+        k[r][0] = src[0]; k[r][1] = src[NT]; k[r][2] = src[2 * NT];
       }
     };
+    issue_kap(zb);
+    issue_kap(zb + 1);
+    issue_kap(zb + 2);
 
     // plane zb-1 -> bot
     tma::mbar_wait(&full[stage], phase);
@@ -219,9 +243,12 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
       for (int r = 0; r < RY; ++r) cen[r] = *reinterpret_cast<const double2 *>(p + r * ROWB);
     }
     advance();
+    tma::cp_async_wait<2>();   // kap(zb) has landed
     load_kap(klo, zb);
 
     for (int z = zb; z < ze; ++z) {
+      issue_kap(z + 3);
+      tma::cp_async_wait<2>();  // kap(z+1) has landed; z+2 and z+3 may be in flight
       load_kap(khi, z + 1);
       const int stage_t = stage;
       tma::mbar_wait(&full[stage], phase);
@@ -295,10 +322,15 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
       }
     }
     release(stage_c);
+    tma::cp_async_wait<0>();  // nothing of this item still lands in the kap slots
   }
 }
 
 constexpr int kTY = 16, kRY = 2, kNBX = 2;
+constexpr int kKapSlots = 3;
+constexpr size_t KapRingBytes() {
+  return (size_t)kKapSlots * (kRY + 1) * 3 * (kNBX * (kTY / kRY) * 32) * sizeof(double);
+}
 
 }  // namespace
 
@@ -344,7 +376,7 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   PstagPlan *p = new PstagPlan();
   p->fn = (const void *)PstagKernel<kTY, kRY, kNBX>;
   const int stages = 4;
-  p->smem = kBarrierBytes + (size_t)stages * kNBX * PstagBoxStride<kTY>();
+  p->smem = kBarrierBytes + (size_t)stages * kNBX * PstagBoxStride<kTY>() + KapRingBytes();
   p->block = (kNBX * (kTY / kRY) + 1) * 32;
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   int occ = 0;
