@@ -68,6 +68,19 @@ static inline __PSB200GenericShape __PSB200GenericShapeFor(const __PSDomain *dom
     }                              \
   }
 
+/* 2-D and 1-D domains (grid z extent is 1) */
+#define __PSB200_FOREACH_POINT2D_BEGIN(dom, x, y)                                            \
+  {                                                                                          \
+    const int x = (dom).local_min[0] + (int)(blockIdx.x * blockDim.x + threadIdx.x);         \
+    const int y = (dom).local_min[1] + (int)(blockIdx.y * blockDim.y + threadIdx.y);         \
+    if (x < (dom).local_max[0] && y < (dom).local_max[1]) {                                  \
+      {
+#define __PSB200_FOREACH_POINT1D_BEGIN(dom, x)                                               \
+  {                                                                                          \
+    const int x = (dom).local_min[0] + (int)(blockIdx.x * blockDim.x + threadIdx.x);         \
+    if (x < (dom).local_max[0]) {                                                            \
+      {
+
 /* Red/black colouring: a point is visited when ((x + y + z + color) & 1) == 0
  * in the reference's sense: x starts at min + ((min&1) ^ ((y+z+color)%2)) and
  * advances by 2. */

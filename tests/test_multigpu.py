@@ -55,6 +55,11 @@ def test_two_gpus_match_oracle(options):
     _run(2, ["diffusion", "himeno", "pstag", "api"], options)
 
 
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
+def test_two_gpus_reference_system_tests():
+    _run(2, ["golden"], "halo=2")
+
+
 @pytest.mark.skipif(_ngpus() < 4, reason="needs at least 4 GPUs")
 def test_four_gpus_match_oracle():
     _run(4, ["diffusion", "himeno", "pstag", "api"], "halo_push=1")
