@@ -68,8 +68,8 @@ struct PstagLayout {
 template <int TY>
 constexpr int PstagBoxStride() { return PstagLayout<TY>::STRIDE; }
 
-template <int TY, int RY, int NBX>
-__global__ void __launch_bounds__((NBX * (TY / RY) + 1) * 32)
+template <int TY, int RY, int NBX, int MINB>
+__global__ void __launch_bounds__((NBX * (TY / RY) + 1) * 32, MINB)
 PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant__ CUtensorMap map_row,
             const __grid_constant__ CUtensorMap map_col, const __grid_constant__ PstagArgs a) {
   using G = Geom<double>;
@@ -326,11 +326,30 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
   }
 }
 
-constexpr int kTY = 16, kRY = 2, kNBX = 2;
 constexpr int kKapSlots = 3;
-constexpr size_t KapRingBytes() {
-  return (size_t)kKapSlots * (kRY + 1) * 3 * (kNBX * (kTY / kRY) * 32) * sizeof(double);
-}
+
+// tile shapes (rows, rows per thread, boxes side by side); selected by option pstag_variant
+struct PstagVariant {
+  int ty, ry, nbx;
+  const void *fn;
+  size_t box_stride;
+};
+#define PSTAG_VARIANT(TY, RY, NBX, MINB) \
+  { TY, RY, NBX, (const void *)PstagKernel<TY, RY, NBX, MINB>, (size_t)PstagBoxStride<TY>() }
+const PstagVariant kPstagVariants[] = {
+    PSTAG_VARIANT(16, 2, 2, 1),  // 0: 16 consumer warps (register-capped at 96: spills)
+    PSTAG_VARIANT(8, 2, 2, 1),   // 1: 8 consumer warps
+    PSTAG_VARIANT(16, 2, 1, 1),  // 2
+    PSTAG_VARIANT(8, 1, 2, 1),   // 3
+    PSTAG_VARIANT(8, 2, 1, 2),   // 4: 4 consumer warps, 128 registers, two CTAs per SM
+    PSTAG_VARIANT(16, 4, 2, 1),  // 5
+    PSTAG_VARIANT(8, 2, 1, 3),   // 6: same shape squeezed to three CTAs per SM
+    PSTAG_VARIANT(8, 2, 1, 4),   // 7: ... four
+    PSTAG_VARIANT(8, 1, 1, 2),   // 8: 8 consumer warps of one row each
+    PSTAG_VARIANT(4, 1, 1, 4),   // 9
+    PSTAG_VARIANT(16, 4, 1, 3),  // 10: 4 consumer warps, 4 rows per thread
+};
+constexpr int kNumPstagVariants = sizeof(kPstagVariants) / sizeof(kPstagVariants[0]);
 
 }  // namespace
 
@@ -365,6 +384,12 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   if (nx % 2 != 0 || dom.local_min[0] % 2 != 0 || dom.local_max[0] % 2 != 0) {
     *why = "x extent and domain x-range must be even"; return nullptr;
   }
+  int vi = rt->opt.pstag_variant;
+  if (vi < 0 || vi >= kNumPstagVariants) vi = 6;
+  // the default tile is 8 rows; grids whose y extent is not a multiple of it try 4 rows
+  if (ny % kPstagVariants[vi].ty != 0 && ny % 4 == 0) vi = 9;
+  const PstagVariant &V = kPstagVariants[vi];
+  const int kTY = V.ty, kRY = V.ry, kNBX = V.nbx;
   if (ny % kTY != 0 || (dom.local_min[1] % kTY) != 0) { *why = "y extent must be a multiple of the tile height"; return nullptr; }
   if (nx < Geom<double>::HX || nz < 1) { *why = "grid too small"; return nullptr; }
   for (int i = 0; i < 3; ++i)
@@ -374,14 +399,19 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   if (dom.local_min[0] != 0) { *why = "domain must start at x = 0"; return nullptr; }
 
   PstagPlan *p = new PstagPlan();
-  p->fn = (const void *)PstagKernel<kTY, kRY, kNBX>;
-  const int stages = 4;
-  p->smem = kBarrierBytes + (size_t)stages * kNBX * PstagBoxStride<kTY>() + KapRingBytes();
+  p->fn = V.fn;
+  int stages = rt->opt.pstag_stages > 0 ? std::min(rt->opt.pstag_stages, kMaxStages) : 6;
+  if (stages < 3) stages = 3;
+  const size_t kap_ring = (size_t)kKapSlots * (kRY + 1) * 3 * (kNBX * (kTY / kRY) * 32) * sizeof(double);
+  while (stages > 3 && kBarrierBytes + (size_t)stages * kNBX * V.box_stride + kap_ring > 227 * 1024)
+    --stages;
+  p->smem = kBarrierBytes + (size_t)stages * kNBX * V.box_stride + kap_ring;
   p->block = (kNBX * (kTY / kRY) + 1) * 32;
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   int occ = 0;
   PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->fn, p->block, p->smem));
   PSB_CHECK(occ > 0, "pstag kernel does not fit on an SM");
+  if (rt->opt.pstag_occ > 0) occ = std::min(occ, rt->opt.pstag_occ);
 
   PstagArgs &a = p->args;
   p->wr_member = wr;

@@ -408,6 +408,9 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "himeno_stages") o->himeno_stages = (int)val;
   else if (k == "himeno_occ") o->himeno_occ = (int)val;
   else if (k == "himeno_carveout") o->himeno_carveout = (int)val;
+  else if (k == "pstag_variant") o->pstag_variant = (int)val;
+  else if (k == "pstag_stages") o->pstag_stages = (int)val;
+  else if (k == "pstag_occ") o->pstag_occ = (int)val;
   else if (k == "time_kernels") o->time_kernels = (int)val;
   else if (k == "halo") o->halo = (int)val;
   else if (k == "halo_push") o->halo_push = (int)val;
