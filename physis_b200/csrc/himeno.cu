@@ -49,6 +49,7 @@ struct HimenoArgs {
   // neighbours' halo planes through the CUDA-IPC mapping; -1 / nullptr on one GPU
   int push_lo_z, push_hi_z;
   float *push_lo, *push_hi;
+  SlabSync sync;  // neighbour ordering fused into the kernel
 };
 
 __device__ __forceinline__ float4 LdStream(const float *p) {
@@ -103,6 +104,7 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
       tma::mbar_init(&empty[s], NW);
     }
     tma::fence_barrier_init();
+    SlabSyncWait(a.sync);
   }
   __syncthreads();
 
@@ -268,6 +270,7 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     stage = next_of(sc);
     phase = (stage == 0) ? (phc ^ 1u) : phc;
   }
+  SlabSyncSignal(a.sync, NW * 32, threadIdx.x == 0);
 }
 
 template <int TY>
@@ -284,6 +287,7 @@ struct HimenoPlan {
   HimenoArgs args;
   const void *fn = nullptr;
   bool pushes = false;  // the kernel itself delivers the halo planes of p1
+  bool syncs = false;   // ... and waits for / signals the neighbours itself
 };
 
 HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string *why) {
@@ -378,10 +382,12 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
   a.stages = stages;
   p->grid = std::min(a.nitems, slots);
   a.push_lo_z = a.push_hi_z = -1;
+  a.sync = SlabSync{};
   if (SlabPushTargets(rt, *g[1], 0, (void **)&a.push_lo, (void **)&a.push_hi, sizeof(float))) {
     a.push_lo_z = g[1]->halo;
     a.push_hi_z = g[1]->halo + g[1]->nz_loc - 1;
     p->pushes = true;
+    if (rt->FillSlabSync(&a.sync)) p->syncs = true;
   }
 
   int dimv[3] = {nx, ny, nz};
@@ -395,11 +401,16 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
 }
 
 void LaunchHimeno(Runtime *rt, HimenoPlan *p) {
+  if (p->syncs) {
+    p->args.sync.wait_epoch = rt->sweep_epoch;
+    p->args.sync.signal_epoch = rt->sweep_epoch + 1;
+  }
   void *args[2] = {&p->tmap, &p->args};
   PSB_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(p->block), args, p->smem, rt->stream));
 }
 
 void DestroyHimeno(HimenoPlan *p) { delete p; }
 bool HimenoPushes(const HimenoPlan *p) { return p->pushes; }
+bool HimenoSyncs(const HimenoPlan *p) { return p->syncs; }
 
 }  // namespace physis_b200

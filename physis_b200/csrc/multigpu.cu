@@ -79,8 +79,19 @@ void Runtime::InitGroup() {
   flags_of_lo = static_cast<uint32_t *>(lo);
   flags_of_hi = static_cast<uint32_t *>(hi);
   ResolveMemOps();
-  if (!g_wait32 || !g_write32) opt.sync_mode = 1;
+  if ((!g_wait32 || !g_write32) && opt.sync_mode == 0) opt.sync_mode = 1;
   sweep_epoch = 0;
+  done_counter = reinterpret_cast<unsigned *>(flags + 16);  // same zeroed allocation
+}
+
+bool Runtime::FillSlabSync(sweep::SlabSync *s) {
+  *s = sweep::SlabSync{};
+  if (world() == 1 || opt.sync_mode != 2) return false;
+  s->flags = flags;
+  s->to_lo = flags_of_lo + 1;  // this rank is the upper neighbour of `lo`
+  s->to_hi = flags_of_hi + 0;
+  s->done = done_counter;
+  return true;
 }
 
 void Runtime::ShutdownGroup() {
@@ -114,7 +125,7 @@ void Runtime::CloseIpc(void *peer) {
 }
 
 void Runtime::WaitNeighbours(uint32_t epoch) {
-  if (opt.sync_mode == 0) {
+  if (opt.sync_mode == 0 && g_wait32) {
     // CU_STREAM_WAIT_VALUE_GEQ compares cyclically, so the counter may wrap
     for (int i = 0; i < 2; ++i) {
       CUresult r = g_wait32((CUstream)stream, (CUdeviceptr)(flags + i), epoch, CU_STREAM_WAIT_VALUE_GEQ);
@@ -128,7 +139,7 @@ void Runtime::WaitNeighbours(uint32_t epoch) {
 
 void Runtime::SignalNeighbours(uint32_t epoch) {
   // this rank is the UPPER neighbour of `lo` (their flags[1]) and the LOWER one of `hi`
-  if (opt.sync_mode == 0) {
+  if (opt.sync_mode == 0 && g_write32) {
     // default flags: all earlier writes of this stream (the sweep's peer stores or the
     // peer copies) are visible before the value lands
     CUresult r = g_write32((CUstream)stream, (CUdeviceptr)(flags_of_lo + 1), epoch, CU_STREAM_WRITE_VALUE_DEFAULT);

@@ -49,6 +49,7 @@ struct PstagArgs {
   int zwrap;
   int push_lo_z, push_hi_z;
   double *push_lo, *push_hi;
+  SlabSync sync;  // neighbour ordering fused into the kernel
 };
 
 __host__ __device__ constexpr int Up128(int v) { return (v + 127) / 128 * 128; }
@@ -98,6 +99,7 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
       tma::mbar_init(&empty[s], NW);
     }
     tma::fence_barrier_init();
+    SlabSyncWait(a.sync);
   }
   __syncthreads();
 
@@ -324,6 +326,7 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
     release(stage_c);
     tma::cp_async_wait<0>();  // nothing of this item still lands in the kap slots
   }
+  SlabSyncSignal(a.sync, NW * 32, threadIdx.x == 0);
 }
 
 constexpr int kKapSlots = 3;
@@ -360,6 +363,7 @@ struct PstagPlan {
   PstagArgs args;
   const void *fn = nullptr;
   bool pushes = false;
+  bool syncs = false;
   int wr_member = 0;
 };
 
@@ -440,10 +444,12 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
     return nullptr;
   }
   a.push_lo_z = a.push_hi_z = -1;
+  a.sync = SlabSync{};
   if (SlabPushTargets(rt, *u, wr, (void **)&a.push_lo, (void **)&a.push_hi, sizeof(double))) {
     a.push_lo_z = u->halo;
     a.push_hi_z = u->halo + u->nz_loc - 1;
     p->pushes = true;
+    if (rt->FillSlabSync(&a.sync)) p->syncs = true;
   }
 
   int dimv[3] = {nx, ny, nz};
@@ -461,11 +467,16 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
 }
 
 void LaunchPstag(Runtime *rt, PstagPlan *p) {
+  if (p->syncs) {
+    p->args.sync.wait_epoch = rt->sweep_epoch;
+    p->args.sync.signal_epoch = rt->sweep_epoch + 1;
+  }
   void *args[4] = {&p->map_main, &p->map_row, &p->map_col, &p->args};
   PSB_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(p->block), args, p->smem, rt->stream));
 }
 
 void DestroyPstag(PstagPlan *p) { delete p; }
 bool PstagPushes(const PstagPlan *p) { return p->pushes; }
+bool PstagSyncs(const PstagPlan *p) { return p->syncs; }
 
 }  // namespace physis_b200

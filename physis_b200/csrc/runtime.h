@@ -21,6 +21,7 @@
 #include "physis/physis_b200.h"
 #include "common.h"
 #include "comm.h"
+#include "sweep_common.cuh"
 
 namespace physis_b200 {
 
@@ -142,7 +143,8 @@ struct Options {
   int halo = 1;          // halo planes per side of decomposed grids
   int halo_push = 1;     // 1: specialised sweeps store their boundary planes straight into
                          //    the neighbour's halo (fused); 0: peer copies after the kernel
-  int sync_mode = 0;     // 0: stream memory operations, 1: signal/wait kernels
+  int sync_mode = 2;     // 2: waits and signals fused into the sweep kernels, 0: stream
+                         //    memory operations, 1: one-thread signal/wait kernels
   int copyout_gather = 1;  // PSGridCopyout fills the whole host array on every rank
 };
 
@@ -188,6 +190,10 @@ class Runtime {
   uint32_t *flags_of_lo = nullptr;   // IPC mappings of the neighbours' flag words
   uint32_t *flags_of_hi = nullptr;
   uint32_t sweep_epoch = 0;          // sweeps enqueued so far (identical on every rank)
+  unsigned *done_counter = nullptr;  // finished-CTA counter of sweeps that signal themselves
+  // fills the device-side view of the flag words for a kernel that waits / signals itself;
+  // false when the run is single-GPU or opt.sync_mode selects stream-ordered flags
+  bool FillSlabSync(sweep::SlabSync *s);
   void InitGroup();
   void ShutdownGroup();
   // stream-ordered: wait until both neighbours have finished sweep `epoch`

@@ -56,6 +56,7 @@ struct Star7Args {
   // mapping, into the ring neighbour's halo plane (fused halo exchange over NVLink)
   int push_lo_z, push_hi_z;
   T *push_lo, *push_hi;
+  SlabSync sync;  // neighbour ordering fused into the kernel (second form only)
 };
 
 template <typename T>
@@ -381,6 +382,7 @@ Star7KernelV2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       tma::mbar_init(&empty[s], NW);
     }
     tma::fence_barrier_init();
+    SlabSyncWait(a.sync);
   }
   __syncthreads();
 
@@ -542,6 +544,7 @@ Star7KernelV2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     }
     if (has_top) S7_RELEASE(stage_c);  // plane ze was loaded as the top plane only
   }
+  SlabSyncSignal(a.sync, NW * 32, threadIdx.x == 0);
 #undef S7_STEP
 #undef S7_LOAD
 #undef S7_RELEASE
@@ -614,6 +617,7 @@ struct Star7Plan {
   Star7Args<double> ad;
   const void *fn = nullptr;
   bool pushes = false;  // the kernel itself delivers the halo planes of `out`
+  bool syncs = false;   // ... and waits for / signals the neighbours itself
 };
 
 template <typename T>
@@ -626,6 +630,7 @@ static void FillArgs(Star7Args<T> *a, const __PSB200StencilDesc &d, const Grid *
   a->zcl_hi = gin->LocalInterior(gin->dim[2] - 1);
   a->push_lo_z = a->push_hi_z = -1;
   a->push_lo = a->push_hi = nullptr;
+  a->sync = SlabSync{};
   a->dx0 = d.dom.local_min[0]; a->dx1 = d.dom.local_max[0];
   a->dy0 = d.dom.local_min[1]; a->dy1 = d.dom.local_max[1];
   a->dz0 = d.dom.local_min[2]; a->dz1 = d.dom.local_max[2];
@@ -751,6 +756,8 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
       a->push_lo_z = gout->halo;
       a->push_hi_z = gout->halo + gout->nz_loc - 1;
       p->pushes = true;
+      // the halo stores are in the kernel, so its ordering with the neighbours can be too
+      if (o.star7_impl != 0 && rt->FillSlabSync(&a->sync)) p->syncs = true;
     }
   };
   if (dbl) { FillArgs(&p->ad, d, gin, gout); common(&p->ad); }
@@ -759,6 +766,11 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
 }
 
 void LaunchStar7(Runtime *rt, Star7Plan *p) {
+  if (p->syncs) {
+    SlabSync &sy = p->is_double ? p->ad.sync : p->af.sync;
+    sy.wait_epoch = rt->sweep_epoch;
+    sy.signal_epoch = rt->sweep_epoch + 1;
+  }
   void *args[2];
   args[0] = &p->tmap;
   args[1] = p->is_double ? (void *)&p->ad : (void *)&p->af;
@@ -767,5 +779,6 @@ void LaunchStar7(Runtime *rt, Star7Plan *p) {
 
 void DestroyStar7(Star7Plan *p) { delete p; }
 bool Star7Pushes(const Star7Plan *p) { return p->pushes; }
+bool Star7Syncs(const Star7Plan *p) { return p->syncs; }
 
 }  // namespace physis_b200

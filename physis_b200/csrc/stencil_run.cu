@@ -18,18 +18,21 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
 void LaunchStar7(Runtime *rt, Star7Plan *p);
 void DestroyStar7(Star7Plan *p);
 bool Star7Pushes(const Star7Plan *p);
+bool Star7Syncs(const Star7Plan *p);
 
 struct HimenoPlan;
 HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string *why);
 void LaunchHimeno(Runtime *rt, HimenoPlan *p);
 void DestroyHimeno(HimenoPlan *p);
 bool HimenoPushes(const HimenoPlan *p);
+bool HimenoSyncs(const HimenoPlan *p);
 
 struct PstagPlan;
 PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *why);
 void LaunchPstag(Runtime *rt, PstagPlan *p);
 void DestroyPstag(PstagPlan *p);
 bool PstagPushes(const PstagPlan *p);
+bool PstagSyncs(const PstagPlan *p);
 
 struct SweepPlan {
   int kind = 0;
@@ -42,6 +45,7 @@ struct SweepPlan {
   __PSDomain dom;              // this rank's part of the domain
   bool empty = false;          // ... which may be nothing
   bool fused_push = false;     // the kernel stores the halo planes of what it writes
+  bool fused_sync = false;     // ... and orders itself with the neighbours (SlabSync)
   // (grid, member) pairs whose halo planes must reach the neighbours after the sweep
   std::vector<std::pair<Grid *, int>> written;
 };
@@ -94,6 +98,7 @@ SweepPlan *PrepareSweep(Runtime *rt, const __PSB200StencilDesc &d_in) {
         p->star7 = PrepareStar7(rt, d, &why);
         if (p->star7) {
           p->fused_push = Star7Pushes(p->star7);
+          p->fused_sync = Star7Syncs(p->star7);
           p->written.push_back({Grid::FromHandle(d.grids[1]), 0});
           return p;
         }
@@ -103,6 +108,7 @@ SweepPlan *PrepareSweep(Runtime *rt, const __PSB200StencilDesc &d_in) {
         p->himeno = PrepareHimeno(rt, d, &why);
         if (p->himeno) {
           p->fused_push = HimenoPushes(p->himeno);
+          p->fused_sync = HimenoSyncs(p->himeno);
           p->written.push_back({Grid::FromHandle(d.grids[1]), 0});
           return p;
         }
@@ -111,6 +117,7 @@ SweepPlan *PrepareSweep(Runtime *rt, const __PSB200StencilDesc &d_in) {
         p->pstag = PreparePstag(rt, d, &why);
         if (p->pstag) {
           p->fused_push = PstagPushes(p->pstag);
+          p->fused_sync = PstagSyncs(p->pstag);
           p->written.push_back({Grid::FromHandle(d.grids[0]), d.members[1]});
           return p;
         }
@@ -148,6 +155,7 @@ SweepPlan *PrepareSweep(Runtime *rt, const __PSB200StencilDesc &d_in) {
     p->dom = d_in.dom;
     p->empty = false;
     p->fused_push = false;
+    p->fused_sync = false;
     p->written.clear();
     if (multi && g0) {
       // the 3-D grid of the sweep that is decomposed decides the cut
@@ -176,7 +184,8 @@ void LaunchSweep(Runtime *rt, SweepPlan *p) {
   const bool multi = rt->world() > 1;
   // neighbours must have finished the previous sweep: their halo stores into this
   // rank are complete, and they no longer read the halo planes this sweep overwrites
-  if (multi) rt->WaitNeighbours(rt->sweep_epoch);
+  const bool self_sync = multi && p->fused_sync && !p->empty;
+  if (multi && !self_sync) rt->WaitNeighbours(rt->sweep_epoch);
   if (!p->empty) {
     if (p->star7) LaunchStar7(rt, p->star7);
     else if (p->himeno) LaunchHimeno(rt, p->himeno);
@@ -187,7 +196,8 @@ void LaunchSweep(Runtime *rt, SweepPlan *p) {
   if (multi) {
     if (!p->fused_push)
       for (auto &w : p->written) rt->PushHalos(*w.first, w.second);
-    rt->SignalNeighbours(++rt->sweep_epoch);
+    ++rt->sweep_epoch;
+    if (!self_sync) rt->SignalNeighbours(rt->sweep_epoch);
   }
 }
 

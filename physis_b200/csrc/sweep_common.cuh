@@ -46,6 +46,58 @@ __device__ __forceinline__ void StoreVec(double2 *p, const double2 &v, bool stre
   if (streaming) __stcs(p, v); else *p = v;
 }
 
+// Neighbour ordering of a multi-GPU sweep, fused into the sweep kernel itself
+// (multigpu.cu): before touching halo planes every CTA waits until both ring
+// neighbours have finished the previous sweep; the last CTA to finish publishes this
+// sweep's number into the neighbours' flag words (peer memory, NVLink).  All null /
+// zero on one GPU.
+struct SlabSync {
+  const uint32_t *flags;   // this rank's two flag words: [0] written by lo, [1] by hi
+  uint32_t *to_lo;         // lo neighbour's flags[1]
+  uint32_t *to_hi;         // hi neighbour's flags[0]
+  unsigned *done;          // CTAs of this launch that have finished (self-resetting)
+  uint32_t wait_epoch;     // neighbours must have completed this many sweeps
+  uint32_t signal_epoch;   // the number this sweep publishes
+};
+
+__device__ __forceinline__ uint32_t LdAcquireSys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void StReleaseSys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Called by thread 0 of every CTA before the CTA's first __syncthreads().
+__device__ __forceinline__ void SlabSyncWait(const SlabSync &s) {
+  if (!s.flags) return;
+  for (int i = 0; i < 2; ++i) {
+    uint32_t spins = 0;
+    while ((int32_t)(LdAcquireSys(s.flags + i) - s.wait_epoch) < 0) {
+      __nanosleep(64);
+      if (++spins > (1u << 26)) __trap();  // a lost signal becomes an error, not a hang
+    }
+  }
+}
+
+// Called by every consumer thread after its last store; `nthreads` consumer threads
+// take part (a multiple of 32), `leader` is true for exactly one of them.
+__device__ __forceinline__ void SlabSyncSignal(const SlabSync &s, int nthreads, bool leader) {
+  if (!s.done) return;
+  __threadfence_system();  // this thread's stores (incl. peer stores) are visible system-wide
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+  if (leader) {
+    const unsigned prev = atomicAdd(s.done, 1u);
+    if (prev == gridDim.x - 1) {
+      *s.done = 0;           // next launch starts from zero (stream order)
+      __threadfence_system();
+      StReleaseSys(s.to_lo, s.signal_epoch);
+      StReleaseSys(s.to_hi, s.signal_epoch);
+    }
+  }
+}
+
 constexpr int kBarrierBytes = 128;  // full[] + empty[], up to 8 stages
 constexpr int kMaxStages = 8;
 

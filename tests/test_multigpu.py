@@ -50,7 +50,8 @@ def _run(world, cases, options=""):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("options", ["halo_push=1", "halo_push=0", "halo_push=1,sync_mode=1"])
+@pytest.mark.parametrize("options", ["halo_push=1", "halo_push=0", "halo_push=1,sync_mode=1",
+                                     "halo_push=1,sync_mode=0", "halo_push=0,sync_mode=0"])
 def test_two_gpus_match_oracle(options):
     _run(2, ["diffusion", "himeno", "pstag", "api"], options)
 
