@@ -592,7 +592,7 @@ const VariantInfo kVariants[] = {
     VARIANT_FR(16, 2, 2, 1),  // 14: full rows of 2 boxes
     VARIANT_FR(8, 4, 8, 1),   // 15: full rows of 8 boxes (1024 floats)
     VARIANT_FR(8, 2, 2, 2),   // 16
-    VARIANT_FR(16, 4, 8, 1),  // 17
+    VARIANT_FR(16, 4, 2, 2),  // 17
     VARIANT_FR(8, 1, 2, 1),   // 18
     VARIANT_FR(8, 2, 1, 4),   // 19: one box
 };
@@ -706,6 +706,7 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
     --stages;
   p->smem = dbl ? SmemBytes<double>(v, stages) : SmemBytes<float>(v, stages);
   p->block = (v.nbx * (v.ty / v.ry) + 1) * 32;
+  PSB_CHECK(p->block <= 1024, "star7 tile shape needs more than 1024 threads");
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 cudaSharedmemCarveoutMaxShared));
