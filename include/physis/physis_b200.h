@@ -302,6 +302,7 @@ typedef struct {
   uint64_t d2h_bytes;
   uint64_t halo_bytes;
   float last_kernel_ms;   /* mean device ms per launch of the last timed family, 0 if off */
+  uint64_t fused_pairs;   /* of kernel_launches: fused two-sweep passes (two sweeps each) */
 } __PSB200Stats;
 void __PSB200GetStats(__PSB200Stats *out);
 void __PSB200ResetStats(void);

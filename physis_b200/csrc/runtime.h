@@ -135,6 +135,8 @@ struct Options {
   // star-7 sweep tile shape (see star7.cu); 0 = automatic
   int star7_ty = 0, star7_ry = 0, star7_nbx = 0, star7_stages = 0, star7_zc = 0, star7_occ = 0;
   int star7_variant = -1 /* auto */, star7_l2hint = 0, star7_sthint = 0, star7_impl = 2;
+  int star7_fuse = 1;     // 1: a ping-pong pair of whole-grid 7-pt sweeps runs as one fused two-sweep pass
+  int star7_pair_zc = 0;  // z chunk of the fused kernel; 0 = automatic
   int himeno_by = 0, himeno_zc = 0, himeno_stages = 0, himeno_occ = 0, himeno_carveout = 0;
   int pstag_variant = 6 /* measured best, profiles/r1_tune_pstag_512.csv */, pstag_stages = 0, pstag_occ = 0;
   int time_kernels = 0;        // per-family CUDA-event timing (for bench roofline)

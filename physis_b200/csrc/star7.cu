@@ -27,6 +27,7 @@
 #include "runtime.h"
 #include "tma.cuh"
 #include "sweep_common.cuh"
+#include "star7_math.cuh"
 
 #include <algorithm>
 #include <type_traits>
@@ -58,19 +59,6 @@ struct Star7Args {
   T *push_lo, *push_hi;
   SlabSync sync;  // neighbour ordering fused into the kernel (second form only)
 };
-
-template <typename T>
-__device__ __forceinline__ T Point7(const Star7Args<T> &a, T c, T w, T e, T s, T n, T b, T t) {
-  // ((((((cc*c + cw*w) + ce*e) + cs*s) + cn*n) + cb*b) + ct*t)
-  T r = MulRn(a.cc, c);
-  r = AddRn(r, MulRn(a.cw, w));
-  r = AddRn(r, MulRn(a.ce, e));
-  r = AddRn(r, MulRn(a.cs, s));
-  r = AddRn(r, MulRn(a.cn, n));
-  r = AddRn(r, MulRn(a.cb, b));
-  r = AddRn(r, MulRn(a.ct, t));
-  return r;
-}
 
 // TY  rows of the CTA tile, RY rows per thread, NBX boxes side by side in x,
 // MINB resident CTAs per SM the register budget is sized for.
@@ -279,71 +267,6 @@ Star7Kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
 // feeding a packed add into FFMA2 even with explicit .rn, which would change the
 // rounding, so the multiplies stay scalar.)
 
-namespace v2 {
-
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 Pack(float lo, float hi) {
-  u64 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void Unpack(u64 v, float &lo, float &hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ u64 Add2(u64 a, u64 b) {
-  u64 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-
-// out vector from centre c, neighbours: west/east scalars of the vector's ends,
-// and the s, n, b, t vectors.  ((((((cc*c + cw*w) + ce*e) + cs*s) + cn*n) + cb*b) + ct*t)
-template <int FP>
-__device__ __forceinline__ float4 Vec7(const Star7Args<float> &a, float4 c, float wv, float ev,
-                                       float4 s, float4 n, float4 b, float4 t) {
-  float4 o;
-  if (FP == 0) {
-    o.x = Point7<float>(a, c.x, wv, c.y, s.x, n.x, b.x, t.x);
-    o.y = Point7<float>(a, c.y, c.x, c.z, s.y, n.y, b.y, t.y);
-    o.z = Point7<float>(a, c.z, c.y, c.w, s.z, n.z, b.z, t.z);
-    o.w = Point7<float>(a, c.w, c.z, ev, s.w, n.w, b.w, t.w);
-  } else {
-    // separately rounded products, then packed adds in the reference's order
-    u64 r01 = Pack(MulRn(a.cc, c.x), MulRn(a.cc, c.y));
-    u64 r23 = Pack(MulRn(a.cc, c.z), MulRn(a.cc, c.w));
-    r01 = Add2(r01, Pack(MulRn(a.cw, wv), MulRn(a.cw, c.x)));
-    r23 = Add2(r23, Pack(MulRn(a.cw, c.y), MulRn(a.cw, c.z)));
-    r01 = Add2(r01, Pack(MulRn(a.ce, c.y), MulRn(a.ce, c.z)));
-    r23 = Add2(r23, Pack(MulRn(a.ce, c.w), MulRn(a.ce, ev)));
-    r01 = Add2(r01, Pack(MulRn(a.cs, s.x), MulRn(a.cs, s.y)));
-    r23 = Add2(r23, Pack(MulRn(a.cs, s.z), MulRn(a.cs, s.w)));
-    r01 = Add2(r01, Pack(MulRn(a.cn, n.x), MulRn(a.cn, n.y)));
-    r23 = Add2(r23, Pack(MulRn(a.cn, n.z), MulRn(a.cn, n.w)));
-    r01 = Add2(r01, Pack(MulRn(a.cb, b.x), MulRn(a.cb, b.y)));
-    r23 = Add2(r23, Pack(MulRn(a.cb, b.z), MulRn(a.cb, b.w)));
-    r01 = Add2(r01, Pack(MulRn(a.ct, t.x), MulRn(a.ct, t.y)));
-    r23 = Add2(r23, Pack(MulRn(a.ct, t.z), MulRn(a.ct, t.w)));
-    Unpack(r01, o.x, o.y);
-    Unpack(r23, o.z, o.w);
-  }
-  return o;
-}
-template <int FP>
-__device__ __forceinline__ double2 Vec7(const Star7Args<double> &a, double2 c, double wv, double ev,
-                                        double2 s, double2 n, double2 b, double2 t) {
-  double2 o;
-  o.x = Point7<double>(a, c.x, wv, c.y, s.x, n.x, b.x, t.x);
-  o.y = Point7<double>(a, c.y, c.x, ev, s.y, n.y, b.y, t.y);
-  return o;
-}
-
-__device__ __forceinline__ float First(const float4 &v) { return v.x; }
-__device__ __forceinline__ float Last(const float4 &v) { return v.w; }
-__device__ __forceinline__ double First(const double2 &v) { return v.x; }
-__device__ __forceinline__ double Last(const double2 &v) { return v.y; }
-
-}  // namespace v2
 
 // FR ("full row"): the NBX boxes of a tile cover a whole grid row, so boxes carry no
 // x halo (the x neighbours of a box's edge lanes live in the adjacent box of the same

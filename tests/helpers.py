@@ -132,3 +132,33 @@ def run_pstag(lib, u, kap, nx, ny, nz, count):
     lib.pstag_run(count, u.ctypes.data, np.ascontiguousarray(kap).ctypes.data, nx, ny, nz)
     lib.pstag_finalize()
     return u
+
+
+# ---- numpy restatement of the clamped 7-point update (fp32 / fp64) ------------
+
+def diffusion7_numpy(field, shape, coeffs, steps):
+    """`steps` sweeps of kernel_physis (examples/diffusion-benchmark/diffusion3d_physis.c:29-58)
+    in the REFERENCE target's evaluation order: separately rounded products summed left to
+    right, a neighbour outside the grid replaced by the centre.  numpy's elementwise
+    multiply and add round once each (no FMA contraction), so this is bit-identical to the
+    C oracle (checked on CPU by tests/test_oracle.py).  coeffs: ce, cw, cn, cs, ct, cb, cc."""
+    nx, ny, nz = shape
+    dt = np.asarray(field).dtype.type
+    ce, cw, cn, cs, ct, cb, cc = [dt(c) for c in coeffs[:7]]
+    f = np.array(field, copy=True).reshape(nz, ny, nx)
+    for _ in range(steps):
+        w = np.concatenate([f[:, :, :1], f[:, :, :-1]], axis=2)
+        e = np.concatenate([f[:, :, 1:], f[:, :, -1:]], axis=2)
+        n = np.concatenate([f[:, :1, :], f[:, :-1, :]], axis=1)
+        s = np.concatenate([f[:, 1:, :], f[:, -1:, :]], axis=1)
+        b = np.concatenate([f[:1], f[:-1]], axis=0)
+        t = np.concatenate([f[1:], f[-1:]], axis=0)
+        r = cc * f
+        r = r + cw * w
+        r = r + ce * e
+        r = r + cs * s
+        r = r + cn * n
+        r = r + cb * b
+        r = r + ct * t
+        f = r
+    return f.reshape(-1)

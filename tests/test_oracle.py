@@ -194,3 +194,16 @@ def test_diffusion_accuracy_figure_matches_reference():
     err = np.sqrt(np.sum((got.astype(np.float64) - exact.astype(np.float64)) ** 2) / got.size)
     want = float(GOLD["diffusion_baseline"][f"{n}x{count}"]["accuracy"])
     assert abs(err - want) <= 1e-4 * want  # the reference accumulates the squares in its own order
+
+
+@pytest.mark.parametrize("shape,count", [((32, 17, 9), 6), ((64, 8, 5), 4), ((4, 2, 2), 6), ((20, 1, 3), 2)])
+def test_numpy_restatement_equals_c_oracle(shape, count):
+    """helpers.diffusion7_numpy (the checker of the fused two-sweep GPU tests, also used for
+    fp64) is bit-identical to the C restatement of the REFERENCE target."""
+    nx, ny, nz = shape
+    rng = np.random.default_rng(11)
+    f0 = rng.random(nx * ny * nz, dtype=np.float32)
+    co = np.array([0.11, 0.07, 0.13, 0.05, 0.17, 0.03, 0.44], np.float32)
+    want = H.run_diffusion(H.oracle_port(), f0, nx, ny, nz, count, co)
+    got = H.diffusion7_numpy(f0, shape, co, count)
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
