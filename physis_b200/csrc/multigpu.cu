@@ -178,12 +178,12 @@ void Runtime::PushHalos(Grid &g, int member) {
 bool SlabPushTargets(Runtime *rt, const Grid &g, int member, void **to_lo, void **to_hi,
                      size_t elem_size) {
   *to_lo = *to_hi = nullptr;
-  if (!g.decomposed || g.halo != 1 || !rt->opt.halo_push) return false;
+  if (!g.decomposed || g.halo < 1 || !rt->opt.halo_push) return false;
   const MemberLayout &ml = g.members[member];
   if (ml.count != 1 || (size_t)ml.size != elem_size) return false;
   const size_t plane = (size_t)g.plane_elms * ml.size;
   *to_lo = (char *)ml.peer_lo + (size_t)(g.halo + g.lo_nz_loc) * plane;  // their upper halo
-  *to_hi = (char *)ml.peer_hi;                                          // their lower halo
+  *to_hi = (char *)ml.peer_hi + (size_t)(g.halo - 1) * plane;           // their lower halo
   return true;
 }
 

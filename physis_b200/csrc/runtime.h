@@ -137,12 +137,14 @@ struct Options {
   int star7_variant = -1 /* auto */, star7_l2hint = 0, star7_sthint = 0, star7_impl = 2;
   int star7_fuse = 1;     // 1: a ping-pong pair of whole-grid 7-pt sweeps runs as one fused two-sweep pass
   int star7_pair_zc = 0;  // z chunk of the fused kernel; 0 = automatic
+  int star7_pair_dbg = 0; // timing experiments only (results invalid): 1 = no neighbour wait/signal, 2 = no halo stores
   int himeno_by = 0, himeno_zc = 0, himeno_stages = 0, himeno_occ = 0, himeno_carveout = 0;
   int pstag_variant = 6 /* measured best, profiles/r1_tune_pstag_512.csv */, pstag_stages = 0, pstag_occ = 0;
   int time_kernels = 0;        // per-family CUDA-event timing (for bench roofline)
   size_t stage_chunk = 32u << 20;  // pinned staging chunk for pageable copies
   // multi-GPU
-  int halo = 1;          // halo planes per side of decomposed grids
+  int halo = 2;          // halo planes per side of decomposed grids (single sweeps use the one
+                         // next to the interior; the fused two-sweep pass needs two)
   int halo_push = 1;     // 1: specialised sweeps store their boundary planes straight into
                          //    the neighbour's halo (fused); 0: peer copies after the kernel
   int sync_mode = 2;     // 2: waits and signals fused into the sweep kernels, 0: stream
@@ -223,7 +225,7 @@ class Runtime {
 // Where a fused sweep must store its first / last interior plane of (g, member) so
 // that it lands in the ring neighbours' halo planes: base pointers of those planes
 // in the peers' IPC-mapped allocations.  False when the exchange is not fused
-// (one GPU, halo wider than one plane, or opt.halo_push == 0).
+// (one GPU or opt.halo_push == 0); with wider halos it is the plane next to the interior.
 bool SlabPushTargets(Runtime *rt, const Grid &g, int member, void **to_lo, void **to_hi,
                      size_t elem_size);
 

@@ -44,13 +44,32 @@ using namespace sweep;
 template <typename T>
 struct PairArgs {
   T *out;
-  int nx, ny, nz;
+  int nx, ny, nz;        // extents of the (local) allocation; nz includes halo planes
   T cc, cw, ce, cs, cn, cb, ct;
   int nty, nzc, zc, nitems;
   int st_hint;
+  // z-slab view (multi-GPU; on one GPU dz = [0, nz), the faces are planes 0 and nz-1 and
+  // nothing is pushed).  Local plane indices throughout.
+  int dz0, dz1;            // planes this rank computes
+  int zface_lo, zface_hi;  // planes holding the global z faces, or -1 when they are elsewhere
+  int zld_lo, zld_hi;      // plane range loads are clamped to
+  // the first two / last two planes computed here are also stored, through the CUDA-IPC
+  // peer mapping, into the ring neighbours' two halo planes (fused exchange over NVLink)
+  // (as byte distances from the plane's own address in `out`: uniform over the kernel)
+  int push_lo_z, push_hi_z;
+  long long push_lo_delta, push_hi_delta;
+  SlabSync sync;           // neighbour ordering fused into the kernel
 };
 
 constexpr int kPairSlots = 3;
+
+// out of line: the spin loop must not take part in the sweep's register allocation
+__device__ __noinline__ void PairWaitNeighbours(const uint32_t *flags, uint32_t epoch) {
+  SlabSync s{};
+  s.flags = flags;
+  s.wait_epoch = epoch;
+  SlabSyncWait(s);
+}
 
 template <typename T, int NBX, int NWY, int RY>
 struct PairGeom {
@@ -58,13 +77,14 @@ struct PairGeom {
   static constexpr int ROWB = Geom<T>::TXB * (int)sizeof(T);  // 512 bytes: one warp of vectors
   static constexpr int IN_BOX = (H + 2) * ROWB;
   static constexpr int IN_STAGE = NBX * IN_BOX;
-  static constexpr int S1_BOX = H * ROWB;
+  static constexpr int S1_BOX = (H + 2) * ROWB;  // one unused row above and below: edge warps read in bounds
   static constexpr int S1_STAGE = NBX * S1_BOX;
   static constexpr int SMEM = kBarrierBytes + kPairSlots * (IN_STAGE + S1_STAGE);
   static constexpr int THREADS = NBX * NWY * 32;
 };
 
-template <typename T, int NBX, int NWY, int RY, int MINB, int FP>
+// SLAB: the z-slab form (halo planes stored to the ring neighbours, ordering with them)
+template <typename T, int NBX, int NWY, int RY, int MINB, int FP, bool SLAB>
 __global__ void __launch_bounds__(NBX * NWY * 32, MINB)
 Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PairArgs<T> a) {
   using G = Geom<T>;
@@ -93,196 +113,226 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     for (int s = 0; s < NS; ++s) tma::mbar_init(&full[s], 1);
     tma::fence_barrier_init();
     tma::prefetch_tensormap(&tmap);
+    if (SLAB) PairWaitNeighbours(a.sync.flags, a.sync.wait_epoch);  // before any halo plane is read or any peer halo written
   }
 
   const int bx = warp % NBX;
   const int wy = warp / NBX;
   const int j0 = wy * RY;  // tile row of this thread's first row
   const unsigned char *my_in = in_ring + bx * IN_BOX + (j0 + 1) * ROWB + lane * 16;
-  unsigned char *my_s1 = s1_ring + bx * S1_BOX + j0 * ROWB + lane * 16;
+  // the s1 ring has the input ring's geometry, so one base address serves both
+  static_assert(S1_BOX == IN_BOX, "rings share their box geometry");
+  unsigned char *my_s1 = const_cast<unsigned char *>(my_in) + NS * IN_STAGE;
   const bool rd_west = (lane == 0) && (bx > 0);
   const bool rd_east = (lane == 31) && (bx < NBX - 1);
   const int x = bx * G::TXB + lane * VEC;
   const bool x_ok = (x + VEC <= a.nx);
   const bool x_first = (x == 0);
   const bool x_last = (x + VEC == a.nx);
-  // rows of the s1 ring above / below this thread's rows (kept inside the tile)
-  const int s1_north = (wy == 0) ? 0 : -ROWB;
-  const int s1_south = (wy == NWY - 1) ? (RY - 1) * ROWB : RY * ROWB;
   const size_t plane_elems = (size_t)a.nx * a.ny;
   int nbox = 0;
 #pragma unroll
   for (int b = 0; b < NBX; ++b) nbox += (b * G::TXB < a.nx) ? 1 : 0;
   const uint32_t tx_bytes = (uint32_t)nbox * (uint32_t)IN_BOX;
 
-  int stage = 0;       // input ring: slot of the next plane to consume
-  uint32_t phase = 0;
-  int pstage = 0;      // issuer: slot the next plane is loaded into
-  int s1s = 0;         // s1 ring: slot the next first-sweep plane is written to
+  // x neighbours outside a warp's own row segment: lane 0 / the last lane take them from
+  // shared memory -- the adjacent box, or (clamped face) their own edge element
+  const bool need_w = (lane == 0);
+  const bool need_e = x_last || rd_east;
+  const int w_in = rd_west ? -IN_BOX + WEST_EL : 0;
+  const int e_in = x_last ? (VEC - 1) * (int)sizeof(T) : IN_BOX + EAST_EL;
 
-#define SP_ADVANCE() do { if (++stage == NS) { stage = 0; phase ^= 1u; } } while (0)
-#define SP_LOAD(DST, st) do { \
-    const unsigned char *p__ = my_in + (st) * IN_STAGE; \
+  uint32_t par = 0;  // bit s: phase parity of input slot s
+  int pstage = 0;                          // issuer: slot the next plane is loaded into
+
+#define SP_LOAD(DST, SLOT) do { \
+    const unsigned char *p__ = my_in + (SLOT) * IN_STAGE; \
     _Pragma("unroll") for (int r = 0; r < RY; ++r) DST[r] = *reinterpret_cast<const V *>(p__ + r * ROWB); \
   } while (0)
+#define SP_WAIT(SLOT) do { \
+    tma::mbar_wait(&full[(SLOT)], (par >> (SLOT)) & 1u); \
+    par ^= 1u << (SLOT); \
+  } while (0)
+  // planes beyond the z faces are the face planes themselves: the clamp of the first
+  // sweep costs nothing in the loop
 #define SP_ISSUE(yin, zpl) do { \
     tma::mbar_arrive_expect_tx(&full[pstage], tx_bytes); \
     unsigned char *dst__ = in_ring + pstage * IN_STAGE; \
+    const int zz__ = min(max((zpl), a.zld_lo), a.zld_hi); \
     _Pragma("unroll") for (int b = 0; b < NBX; ++b) \
-      if (b * G::TXB < a.nx) tma::load_3d(dst__ + b * IN_BOX, &tmap, &full[pstage], b * G::TXB, (yin), (zpl)); \
+      if (b * G::TXB < a.nx) tma::load_3d(dst__ + b * IN_BOX, &tmap, &full[pstage], b * G::TXB, (yin), zz__); \
     if (++pstage == NS) pstage = 0; \
+  } while (0)
+
+  // Clamped y faces without selects in the row loop: the one row of a thread's register
+  // planes that lies just outside the grid is overwritten with the face row next to it, so
+  // the in-thread neighbour of the face row is the face row itself; the rows above / below
+  // a thread's rows (read from shared memory) are replaced the same way.  Only warps that
+  // touch a y face do anything (y_fix is 0 elsewhere; the loop keeps it a real branch).
+#define SP_YFIX(PL) do { \
+    for (int e__ = y_fix; e__ > 0; --e__) { \
+      const int r_north = -ybase, r_south = a.ny - 1 - ybase; \
+      _Pragma("unroll") for (int r = 1; r < RY; ++r) if (r == r_north) PL[r - 1] = PL[r]; \
+      _Pragma("unroll") for (int r = 0; r < RY - 1; ++r) if (r == r_south) PL[r + 1] = PL[r]; \
+    } \
+  } while (0)
+#define SP_YFIX_NS(NORTH, SOUTH, PL) do { \
+    for (int e__ = y_fix; e__ > 0; --e__) { \
+      if (ybase == 0) NORTH = PL[0]; \
+      if (ybase + RY == a.ny) SOUTH = PL[RY - 1]; \
+    } \
+  } while (0)
+
+  // One plane.  PH = iteration number mod 3 fixes every ring slot at compile time:
+  // the input plane k+2 arrives in slot (PH+2)%3, plane k+1 (the centre of the first
+  // sweep) sits in slot (PH+1)%3, the first-sweep plane k+1 is written to s1 slot PH, the
+  // second sweep reads s1 plane k from slot (PH+2)%3 and plane k-1 from slot (PH+1)%3.
+  // BOT/CEN/TOP and C1/T1 name register sets whose roles rotate with PH.
+#define SP_STEP(PH, BOT, CEN, TOP, C1, T1) do { \
+    SP_WAIT(((PH) + 2) % 3); \
+    SP_LOAD(TOP, ((PH) + 2) % 3); \
+    SP_YFIX(TOP); \
+    { \
+      const unsigned char *cb = my_in + (((PH) + 1) % 3) * IN_STAGE; \
+      V north = *reinterpret_cast<const V *>(cb - ROWB); \
+      V south = *reinterpret_cast<const V *>(cb + RY * ROWB); \
+      SP_YFIX_NS(north, south, CEN); \
+      unsigned char *sp = my_s1 + (PH) * S1_STAGE; \
+      _Pragma("unroll") for (int r = 0; r < RY; ++r) { \
+        const V c = CEN[r]; \
+        T wv = __shfl_up_sync(0xffffffffu, v2::Last(c), 1); \
+        T ev = __shfl_down_sync(0xffffffffu, v2::First(c), 1); \
+        if (need_w) wv = *reinterpret_cast<const T *>(cb + r * ROWB + w_in); \
+        if (need_e) ev = *reinterpret_cast<const T *>(cb + r * ROWB + e_in); \
+        const V nv = (r == 0) ? north : CEN[r > 0 ? r - 1 : 0]; \
+        const V sv = (r == RY - 1) ? south : CEN[r < RY - 1 ? r + 1 : r]; \
+        T1[r] = v2::Vec7<FP>(a, c, wv, ev, sv, nv, BOT[r], TOP[r]); \
+        *reinterpret_cast<V *>(sp + r * ROWB) = T1[r]; \
+      } \
+      SP_YFIX(T1); \
+    } \
+    __syncthreads(); \
+    if (issuer) { \
+      /* thread 0 owns tile row 0: the box starts one row above it */ \
+      if (k == k0 && k + 3 <= ze + 1) SP_ISSUE(ybase - 1, k + 3); \
+      if (k + 4 <= ze + 1) SP_ISSUE(ybase - 1, k + 4); \
+    } \
+    if (k >= zb) { \
+      const unsigned char *cb = my_s1 + (((PH) + 2) % 3) * S1_STAGE; \
+      /* bottom plane: s1 plane k-1, or (z face) the centre plane itself */ \
+      const unsigned char *bb = (k == a.zface_lo) ? cb : my_s1 + (((PH) + 1) % 3) * S1_STAGE; \
+      V north = *reinterpret_cast<const V *>(cb - ROWB); \
+      V south = *reinterpret_cast<const V *>(cb + RY * ROWB); \
+      SP_YFIX_NS(north, south, C1); \
+      /* top plane beyond the z face: the centre plane (rare: a loop keeps it a branch) */ \
+      for (int e__ = (k == a.zface_hi) ? 1 : 0; e__ > 0; --e__) { \
+        _Pragma("unroll") for (int r = 0; r < RY; ++r) T1[r] = C1[r]; \
+      } \
+      _Pragma("unroll") for (int r = 0; r < RY; ++r) { \
+        const V c = C1[r]; \
+        T wv = __shfl_up_sync(0xffffffffu, v2::Last(c), 1); \
+        T ev = __shfl_down_sync(0xffffffffu, v2::First(c), 1); \
+        if (need_w) wv = *reinterpret_cast<const T *>(cb + r * ROWB + w_in); \
+        if (need_e) ev = *reinterpret_cast<const T *>(cb + r * ROWB + e_in); \
+        const V nv = (r == 0) ? north : C1[r > 0 ? r - 1 : 0]; \
+        const V sv = (r == RY - 1) ? south : C1[r < RY - 1 ? r + 1 : r]; \
+        const V bv = *reinterpret_cast<const V *>(bb + r * ROWB); \
+        const V o = v2::Vec7<FP>(a, c, wv, ev, sv, nv, bv, T1[r]); \
+        if (st_ok[r]) StoreVec(reinterpret_cast<V *>(obase + (size_t)r * a.nx), o, a.st_hint != 0); \
+      } \
+      if (SLAB) { \
+        /* the slab's first two / last two planes also go to the ring neighbours' halos: each \
+           thread forwards the vectors it has just stored (a rare path kept out of the row \
+           loop; a thread reading back its own stores needs no fence) */ \
+        const long long pushd = ((unsigned)(k - a.push_lo_z) < 2u) ? a.push_lo_delta \
+                              : ((unsigned)(k - a.push_hi_z) < 2u) ? a.push_hi_delta : 0ll; \
+        for (int e__ = pushd ? 1 : 0; e__ > 0; --e__) { \
+          _Pragma("unroll") for (int r = 0; r < RY; ++r) { \
+            if (st_ok[r]) { \
+              V *src__ = reinterpret_cast<V *>(obase + (size_t)r * a.nx); \
+              *reinterpret_cast<V *>(reinterpret_cast<char *>(src__) + pushd) = *src__; \
+            } \
+          } \
+        } \
+      } \
+      obase += plane_elems; \
+    } \
   } while (0)
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
     const int zci = item / a.nty;
     const int ty = item - zci * a.nty;
-    const int zb = zci * a.zc;
-    const int ze = min(zb + a.zc, a.nz);
-    const int k0 = zb > 0 ? zb - 2 : -1;  // first plane of the input window
-    const int plast = ze + 1;             // last input plane this item touches
+    const int zb = a.dz0 + zci * a.zc;
+    const int ze = min(zb + a.zc, a.dz1);
+    const int k0 = (zb == a.zface_lo) ? zb - 1 : zb - 2;  // first plane of the input window
     const int y1 = ty * (H - 2) - 1;      // grid row of tile row 0
     const int ybase = y1 + j0;
-    // rows whose y neighbour leaves the grid take the centre value (warp-uniform)
-    const int r_north = -ybase;
-    const int r_south = a.ny - 1 - ybase;
-    const bool y_edge = (r_north >= 0 && r_north < RY) || (r_south >= 0 && r_south < RY);
+    // warps holding a y face row (y == 0 or y == ny-1) fix their planes up (warp-uniform)
+    const int y_fix = ((ybase <= 0 && ybase > -RY) || (ybase <= a.ny - 1 && ybase + RY > a.ny - 1)) ? 1 : 0;
     bool st_ok[RY];
-    T *outp[RY];
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
       const int j = j0 + r;
       const int y = ybase + r;
       st_ok[r] = x_ok && j >= 1 && j <= H - 2 && y >= 0 && y < a.ny;
-      outp[r] = a.out + ((size_t)zb * a.ny + y) * a.nx + x;
     }
+    // second-sweep row 0 of this thread in plane zb (never dereferenced outside the grid)
+    T *obase = a.out + (ptrdiff_t)zb * (ptrdiff_t)plane_elems + (ptrdiff_t)ybase * a.nx + x;
 
-    // every thread is done with both rings of the previous item
+    // every thread is done with both rings of the previous item; slots restart at 0
     __syncthreads();
-    int pnext = k0;
     if (issuer) {
-      for (int n = 0; n < NS; ++n) { SP_ISSUE(y1 - 1, pnext); ++pnext; }
+      pstage = 0;
+      for (int n = 0; n < NS; ++n) SP_ISSUE(ybase - 1, k0 + n);
     }
 
-    V bot[RY], cen[RY], top[RY];  // input window: planes k, k+1, k+2 (own cells)
-    V c1[RY], t1[RY];             // first-sweep planes k and k+1 (own cells)
-    tma::mbar_wait(&full[stage], phase);
-    SP_LOAD(bot, stage);
-    SP_ADVANCE();
-    int stage_c = stage;
-    tma::mbar_wait(&full[stage], phase);
-    SP_LOAD(cen, stage);
-    SP_ADVANCE();
+    V w0[RY], w1[RY], w2[RY];  // input window (own cells); roles rotate, registers do not move
+    V q0[RY], q1[RY], q2[RY];  // first-sweep planes (own cells); two of the three are live
+    SP_WAIT(0);
+    SP_LOAD(w0, 0);
+    SP_YFIX(w0);
+    SP_WAIT(1);
+    SP_LOAD(w1, 1);
+    SP_YFIX(w1);
 #pragma unroll
-    for (int r = 0; r < RY; ++r) c1[r] = cen[r];  // defined value; selected by no store
+    for (int r = 0; r < RY; ++r) q2[r] = w1[r];  // defined value; selected by no store
 
-    for (int k = k0; k < ze; ++k) {
-      // ---------------- first sweep of plane p = k+1 -> t1, s1 ring slot s1s
-      const int p = k + 1;
-      const int stage_t = stage;
-      tma::mbar_wait(&full[stage], phase);
-      SP_LOAD(top, stage);
-      SP_ADVANCE();
-      if (p == 0) {
-#pragma unroll
-        for (int r = 0; r < RY; ++r) bot[r] = cen[r];
-      }
-      if (p == a.nz - 1) {
-#pragma unroll
-        for (int r = 0; r < RY; ++r) top[r] = cen[r];
-      }
-      {
-        const unsigned char *cb = my_in + stage_c * IN_STAGE;
-        const V north = *reinterpret_cast<const V *>(cb - ROWB);
-        const V south = *reinterpret_cast<const V *>(cb + RY * ROWB);
-        unsigned char *sp = my_s1 + s1s * S1_STAGE;
-#pragma unroll
-        for (int r = 0; r < RY; ++r) {
-          const V c = cen[r];
-          T wv = __shfl_up_sync(0xffffffffu, v2::Last(c), 1);
-          T ev = __shfl_down_sync(0xffffffffu, v2::First(c), 1);
-          if (rd_west) wv = *reinterpret_cast<const T *>(cb + r * ROWB - IN_BOX + WEST_EL);
-          if (rd_east) ev = *reinterpret_cast<const T *>(cb + r * ROWB + IN_BOX + EAST_EL);
-          if (x_first) wv = v2::First(c);
-          if (x_last) ev = v2::Last(c);
-          V nv = (r == 0) ? north : cen[r > 0 ? r - 1 : 0];
-          V sv = (r == RY - 1) ? south : cen[r < RY - 1 ? r + 1 : r];
-          if (y_edge) {
-            if (r == r_north) nv = c;
-            if (r == r_south) sv = c;
-          }
-          t1[r] = v2::Vec7<FP>(a, c, wv, ev, sv, nv, bot[r], top[r]);
-          *reinterpret_cast<V *>(sp + r * ROWB) = t1[r];
-        }
-      }
-      __syncthreads();
-      // planes up to k+1 are dead: re-arm their slots
-      if (issuer) {
-        if (k == k0 && pnext <= plast) { SP_ISSUE(y1 - 1, pnext); ++pnext; }
-        if (pnext <= plast) { SP_ISSUE(y1 - 1, pnext); ++pnext; }
-      }
-      // ---------------- second sweep of plane k from s1 planes k-1, k, k+1
-      if (k >= zb) {
-        const int slot_c = (s1s + 2) % NS;   // s1 plane k
-        const int slot_b = (s1s + 1) % NS;   // s1 plane k-1
-        const unsigned char *cb = my_s1 + slot_c * S1_STAGE;
-        const unsigned char *bb = my_s1 + slot_b * S1_STAGE;
-        const V north = *reinterpret_cast<const V *>(cb + s1_north);
-        const V south = *reinterpret_cast<const V *>(cb + s1_south);
-        const bool z_first = (k == 0), z_last = (k == a.nz - 1);
-#pragma unroll
-        for (int r = 0; r < RY; ++r) {
-          const V c = c1[r];
-          T wv = __shfl_up_sync(0xffffffffu, v2::Last(c), 1);
-          T ev = __shfl_down_sync(0xffffffffu, v2::First(c), 1);
-          if (rd_west) wv = *reinterpret_cast<const T *>(cb + r * ROWB - S1_BOX + WEST_EL);
-          if (rd_east) ev = *reinterpret_cast<const T *>(cb + r * ROWB + S1_BOX + EAST_EL);
-          if (x_first) wv = v2::First(c);
-          if (x_last) ev = v2::Last(c);
-          V nv = (r == 0) ? north : c1[r > 0 ? r - 1 : 0];
-          V sv = (r == RY - 1) ? south : c1[r < RY - 1 ? r + 1 : r];
-          if (y_edge) {
-            if (r == r_north) nv = c;
-            if (r == r_south) sv = c;
-          }
-          V bv = *reinterpret_cast<const V *>(bb + r * ROWB);
-          V tv = t1[r];
-          if (z_first) bv = c;
-          if (z_last) tv = c;
-          const V o = v2::Vec7<FP>(a, c, wv, ev, sv, nv, bv, tv);
-          if (st_ok[r]) StoreVec(reinterpret_cast<V *>(outp[r]), o, a.st_hint != 0);
-          outp[r] += plane_elems;
-        }
-      }
-      // rotate the windows
-#pragma unroll
-      for (int r = 0; r < RY; ++r) {
-        bot[r] = cen[r];
-        cen[r] = top[r];
-        c1[r] = t1[r];
-      }
-      stage_c = stage_t;
-      if (++s1s == NS) s1s = 0;
+    int k = k0;
+    for (;;) {
+      SP_STEP(0, w0, w1, w2, q2, q0);
+      if (++k >= ze) break;
+      SP_STEP(1, w1, w2, w0, q0, q1);
+      if (++k >= ze) break;
+      SP_STEP(2, w2, w0, w1, q1, q2);
+      if (++k >= ze) break;
     }
   }
+  if (SLAB) SlabSyncSignal(a.sync, PG::THREADS, threadIdx.x == 0);
+#undef SP_STEP
+#undef SP_YFIX_NS
+#undef SP_YFIX
 #undef SP_ISSUE
+#undef SP_WAIT
 #undef SP_LOAD
-#undef SP_ADVANCE
 }
 
 // ------------------------------------------------------------------ host side
 
 struct PairVariant {
   int nbx, nwy, ry, minb;
-  const void *f32[2];  // scalar / packed-add arithmetic
-  const void *f64;
+  const void *f32[2][2];  // [one GPU / z-slab][scalar / packed-add arithmetic]
+  const void *f64[2];
   int smem_f32, smem_f64, threads;
 };
 
 #define PAIR_VARIANT(NBX, NWY, RY, MINB) \
   { NBX, NWY, RY, MINB, \
-    {(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0>, \
-     (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1>}, \
-    (const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0>, \
+    {{(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0, false>, \
+      (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, false>}, \
+     {(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0, true>, \
+      (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, true>}}, \
+    {(const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, false>, \
+     (const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, true>}, \
     PairGeom<float, NBX, NWY, RY>::SMEM, PairGeom<double, NBX, NWY, RY>::SMEM, NBX * NWY * 32 }
 
 const PairVariant kPairVariants[] = {
@@ -311,7 +361,6 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
                                 const __PSB200StencilDesc &d1, std::string *why) {
   const Options &o = rt->opt;
   if (!o.star7_fuse) { *why = "star7_fuse=0"; return nullptr; }
-  if (rt->world() > 1) { *why = "multi-GPU runs exchange a one-plane halo per sweep"; return nullptr; }
   if (d0.kind != PSB200_KIND_DIFFUSION7_CLAMP || d1.kind != PSB200_KIND_DIFFUSION7_CLAMP) {
     *why = "not a pair of clamped 7-point sweeps"; return nullptr;
   }
@@ -336,10 +385,26 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
       *why = "both sweeps must cover the whole grid"; return nullptr;
     }
   }
+  const bool multi = rt->world() > 1;
+  sweep::SlabSync sync{};
+  if (multi) {
+    // a fused pass consumes two halo planes per side and delivers two; every rank must
+    // take the same decision, so only group-wide quantities enter it
+    if (!ga->decomposed || !gb->decomposed || ga->halo < 2 || gb->halo != ga->halo ||
+        ga->z_off != gb->z_off || ga->nz_loc != gb->nz_loc) {
+      *why = "z-slabs need two halo planes (option halo>=2) and identical cuts"; return nullptr;
+    }
+    if (ga->dim[2] / rt->world() < 4) { *why = "z-slabs thinner than four planes"; return nullptr; }
+    if (!o.halo_push || !rt->FillSlabSync(&sync)) {
+      *why = "needs the in-kernel halo exchange (halo_push=1, sync_mode=2)"; return nullptr;
+    }
+  }
   const bool dbl = ga->type == PS_DOUBLE;
   const int vec = dbl ? 2 : 4;
   const int txb = dbl ? Geom<double>::TXB : Geom<float>::TXB;
-  const int nx = ga->dim[0], ny = ga->dim[1], nz = ga->dim[2];
+  const int nx = ga->dim[0], ny = ga->dim[1];
+  const int nz = ga->nz_loc;         // planes this rank computes
+  const int nz_alloc = ga->ldim[2];  // ... out of this many allocated (halo planes included)
   if (nx % vec != 0) { *why = "x extent must be a multiple of 16 bytes"; return nullptr; }
   const int boxes = CeilDiv(nx, txb);
   int variant = -1;
@@ -351,7 +416,7 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
 
   Star7PairPlan *p = new Star7PairPlan();
   p->is_double = dbl;
-  p->fn = dbl ? v.f64 : v.f32[o.star7_impl == 2 ? 1 : 0];
+  p->fn = dbl ? v.f64[multi ? 1 : 0] : v.f32[multi ? 1 : 0][o.star7_impl == 2 ? 1 : 0];
   p->smem = dbl ? v.smem_f64 : v.smem_f32;
   p->block = v.threads;
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
@@ -383,7 +448,7 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
   Grid *gin[2] = {ga, gb};
   Grid *gout[2] = {gb, ga};
   for (int dir = 0; dir < 2; ++dir) {
-    int dimv[3] = {nx, ny, nz};
+    int dimv[3] = {nx, ny, nz_alloc};
     int boxv[3] = {txb, h + 2, 1};
     if (!EncodeTensorMap3D(&p->tmap[dir], dbl ? TmaElem::F64 : TmaElem::F32, gin[dir]->members[0].dev,
                            dimv, boxv)) {
@@ -394,7 +459,30 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
     auto fill = [&](auto *a) {
       using ET = typename std::remove_pointer<decltype(a->out)>::type;
       a->out = (ET *)gout[dir]->members[0].dev;
-      a->nx = nx; a->ny = ny; a->nz = nz;
+      a->nx = nx; a->ny = ny; a->nz = nz_alloc;
+      a->dz0 = ga->halo; a->dz1 = ga->halo + nz;
+      a->zface_lo = ga->LocalInterior(0);
+      a->zface_hi = ga->LocalInterior(ga->dim[2] - 1);
+      a->zld_lo = a->zface_lo >= 0 ? a->zface_lo : 0;
+      a->zld_hi = a->zface_hi >= 0 ? a->zface_hi : nz_alloc - 1;
+      a->push_lo_z = a->push_hi_z = -(1 << 30);
+      a->push_lo_delta = a->push_hi_delta = 0;
+      a->sync = sync;
+      if (multi) {
+        const Grid *go = gout[dir];
+        const MemberLayout &ml = go->members[0];
+        const size_t plane = (size_t)go->plane_elms;
+        // lower neighbour's two upper halo planes <- my first two planes; upper neighbour's
+        // two lower halo planes (the ones next to its interior) <- my last two planes
+        a->push_lo_z = a->dz0;
+        a->push_hi_z = a->dz1 - 2;
+        const ET *to_lo = (ET *)ml.peer_lo + (size_t)(go->halo + go->lo_nz_loc) * plane;
+        const ET *to_hi = (ET *)ml.peer_hi + (size_t)(go->halo - 2) * plane;
+        a->push_lo_delta = (const char *)to_lo - (const char *)(a->out + (size_t)a->push_lo_z * plane);
+        a->push_hi_delta = (const char *)to_hi - (const char *)(a->out + (size_t)a->push_hi_z * plane);
+        if (o.star7_pair_dbg & 1) a->sync = sweep::SlabSync{};
+        if (o.star7_pair_dbg & 2) a->push_lo_z = a->push_hi_z = -(1 << 30);
+      }
       // scalars arrive in the kernel's parameter order: ce, cw, cn, cs, ct, cb, cc
       a->ce = (ET)d0.scalars[0]; a->cw = (ET)d0.scalars[1]; a->cn = (ET)d0.scalars[2];
       a->cs = (ET)d0.scalars[3]; a->ct = (ET)d0.scalars[4]; a->cb = (ET)d0.scalars[5];
@@ -408,6 +496,11 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
 }
 
 void LaunchStar7Pair(Runtime *rt, Star7PairPlan *p, int dir) {
+  if (rt->world() > 1) {
+    sweep::SlabSync &sy = p->is_double ? p->ad[dir].sync : p->af[dir].sync;
+    sy.wait_epoch = rt->sweep_epoch;
+    sy.signal_epoch = rt->sweep_epoch + 1;
+  }
   void *args[2];
   args[0] = &p->tmap[dir];
   args[1] = p->is_double ? (void *)&p->ad[dir] : (void *)&p->af[dir];

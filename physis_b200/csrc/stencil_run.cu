@@ -252,8 +252,18 @@ extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200St
     pair = PrepareStar7Pair(rt, descs[0], descs[1], &why);
     if (pair) {
       first_unfused = (iter - 1) & ~1;
+      const bool multi = rt->world() > 1;
+      if (multi) {
+        // single sweeps keep only the halo plane next to the interior current; a fused
+        // pass reads two, so the input grid's halos are refreshed once per run
+        rt->WaitNeighbours(rt->sweep_epoch);
+        rt->PushAllHalos(*Grid::FromHandle(descs[0].grids[0]));
+        ++rt->sweep_epoch;
+        rt->SignalNeighbours(rt->sweep_epoch);
+      }
       for (int i = 0; i < first_unfused; ++i) {
         LaunchStar7Pair(rt, pair, i & 1);
+        if (multi) ++rt->sweep_epoch;
         rt->stats.kernel_launches++;
         rt->stats.fused_pairs++;
       }

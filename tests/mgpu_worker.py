@@ -34,6 +34,48 @@ def case_diffusion():
         check(f"diffusion generic {nx}x{ny}x{nz}", want, got, np.uint32)
 
 
+def case_pair():
+    """The fused two-sweep pass on z-slabs: two halo planes per side, delivered by the kernel."""
+    from physis_b200 import api
+    co64 = np.array([0.11, 0.07, 0.13, 0.05, 0.17, 0.03, 0.44])
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cases = [((128, 32, 16), 3, np.float32, ()), ((256, 20, 33), 5, np.float32, ("star7_pair_zc=3",)),
+             ((512, 17, 24), 4, np.float32, ()), ((64, 30, 19), 6, np.float64, ("star7_pair_zc=2",)),
+             ((384, 9, 41), 3, np.float32, ("star7_impl=1",))]
+    for shape, iters, dtype, opts in cases:
+        nx, ny, nz = shape
+        api.PSInit(["t"], 3, shape)
+        for kv in opts:
+            api.set_option(kv)
+        pt = api.PS_FLOAT if dtype == np.float32 else api.PS_DOUBLE
+        a, b = api.Grid(shape, pt), api.Grid(shape, pt)
+        rng = np.random.default_rng(nx + 3 * nz)
+        f0 = rng.random(nx * ny * nz).astype(dtype)
+        a.copyin(f0)
+        b.copyin(rng.random(nx * ny * nz).astype(dtype))
+        dom = api.PSDomain3DNew(0, nx, 0, ny, 0, nz)
+        co = [float(dtype(c)) for c in co64]
+        d0 = api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, dom, [a, b], co, elm_type=pt)
+        d1 = api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, dom, [b, a], co, elm_type=pt)
+        api.rt().__PSB200ResetStats()
+        for rep in range(2):   # the second run starts from halos left by single sweeps
+            api.stencil_run(iters, [d0, d1])
+        pairs = int(api.stats().fused_pairs)
+        envopt = os.environ.get("PHYSIS_B200_OPTIONS", "")
+        in_kernel_exchange = "halo_push=0" not in envopt and "sync_mode=0" not in envopt and "sync_mode=1" not in envopt
+        if world == 1 or (nz // world >= 4 and in_kernel_exchange):
+            assert pairs == 2 * ((iters - 1) & ~1), (shape, pairs)
+        else:
+            assert pairs == 0, (shape, pairs)
+        fa, fb = a.copyout(), b.copyout()
+        view = np.uint32 if dtype == np.float32 else np.uint64
+        check(f"pair A {shape}", H.diffusion7_numpy(f0, shape, co64.astype(dtype), 4 * iters), fa, view)
+        check(f"pair B {shape}", H.diffusion7_numpy(f0, shape, co64.astype(dtype), 4 * iters - 1), fb, view)
+        a.free()
+        b.free()
+        api.PSFinalize()
+
+
 def case_himeno():
     for dims, nn in [((64, 32, 32), 4), ((128, 20, 13), 2)]:
         a = H.run_himeno(H.oracle_port(), dims, nn, gosa=True, seed=5)
@@ -109,7 +151,7 @@ def case_golden():
         assert G.sha(G.stdout_of(n, got)) == G.GOLD[n]["sha256"], n
 
 
-CASES = {"golden": case_golden, "diffusion": case_diffusion, "himeno": case_himeno, "pstag": case_pstag, "api": case_api}
+CASES = {"golden": case_golden, "diffusion": case_diffusion, "pair": case_pair, "himeno": case_himeno, "pstag": case_pstag, "api": case_api}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

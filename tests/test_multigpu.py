@@ -53,7 +53,7 @@ def _run(world, cases, options=""):
 @pytest.mark.parametrize("options", ["halo_push=1", "halo_push=0", "halo_push=1,sync_mode=1",
                                      "halo_push=1,sync_mode=0", "halo_push=0,sync_mode=0"])
 def test_two_gpus_match_oracle(options):
-    _run(2, ["diffusion", "himeno", "pstag", "api"], options)
+    _run(2, ["diffusion", "pair", "himeno", "pstag", "api"], options)
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
@@ -63,14 +63,19 @@ def test_two_gpus_reference_system_tests():
 
 @pytest.mark.skipif(_ngpus() < 4, reason="needs at least 4 GPUs")
 def test_four_gpus_match_oracle():
-    _run(4, ["diffusion", "himeno", "pstag", "api"], "halo_push=1")
+    _run(4, ["diffusion", "pair", "himeno", "pstag", "api"], "halo_push=1")
 
 
 @pytest.mark.skipif(_ngpus() < 3, reason="needs at least 3 GPUs")
 def test_three_gpus_uneven_slabs():
-    _run(3, ["diffusion", "pstag", "api"], "halo_push=0")
+    _run(3, ["diffusion", "pair", "pstag", "api"], "halo_push=0")
+
+
+@pytest.mark.skipif(_ngpus() < 3, reason="needs at least 3 GPUs")
+def test_three_gpus_fused_pairs_uneven_slabs():
+    _run(3, ["pair", "diffusion"], "halo_push=1")
 
 
 def test_single_process_group_of_one():
     # WORLD_SIZE=1 through the same launcher path
-    _run(1, ["diffusion", "api"], "")
+    _run(1, ["diffusion", "pair", "api"], "")
