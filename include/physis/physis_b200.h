@@ -303,6 +303,8 @@ typedef struct {
   uint64_t halo_bytes;
   float last_kernel_ms;   /* mean device ms per launch of the last timed family, 0 if off */
   uint64_t fused_pairs;   /* of kernel_launches: fused two-sweep passes (two sweeps each) */
+  uint64_t fused_pairs_timed; /* with option time_kernels=1: passes covered by fused_pair_ms */
+  double fused_pair_ms;       /* ... and their accumulated device time (CUDA events) */
 } __PSB200Stats;
 void __PSB200GetStats(__PSB200Stats *out);
 void __PSB200ResetStats(void);

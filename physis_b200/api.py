@@ -51,7 +51,8 @@ class StencilDesc(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("halo_bytes", C.c_uint64),
-                ("last_kernel_ms", C.c_float), ("fused_pairs", C.c_uint64)]
+                ("last_kernel_ms", C.c_float), ("fused_pairs", C.c_uint64),
+                ("fused_pairs_timed", C.c_uint64), ("fused_pair_ms", C.c_double)]
 
 
 # every extern "C" symbol include/physis/physis_b200.h declares

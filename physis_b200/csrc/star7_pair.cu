@@ -135,12 +135,12 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   for (int b = 0; b < NBX; ++b) nbox += (b * G::TXB < a.nx) ? 1 : 0;
   const uint32_t tx_bytes = (uint32_t)nbox * (uint32_t)IN_BOX;
 
-  // x neighbours outside a warp's own row segment: lane 0 / the last lane take them from
-  // shared memory -- the adjacent box, or (clamped face) their own edge element
-  const bool need_w = (lane == 0);
-  const bool need_e = x_last || rd_east;
-  const int w_in = rd_west ? -IN_BOX + WEST_EL : 0;
-  const int e_in = x_last ? (VEC - 1) * (int)sizeof(T) : IN_BOX + EAST_EL;
+  // x neighbours of a thread's vector come from shared memory (the centre plane of either
+  // sweep is there): the element before / after the vector, which for lane 0 / lane 31
+  // lives in the adjacent box and on a clamped x face is the vector's own edge element.
+  // One scalar load per side, no shuffles, no predicates.
+  const int w_in = x_first ? 0 : rd_west ? -IN_BOX + WEST_EL : -(int)sizeof(T);
+  const int e_in = x_last ? (VEC - 1) * (int)sizeof(T) : rd_east ? IN_BOX + EAST_EL : VEC * (int)sizeof(T);
 
   uint32_t par = 0;  // bit s: phase parity of input slot s
   int pstage = 0;                          // issuer: slot the next plane is loaded into
@@ -200,10 +200,8 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       unsigned char *sp = my_s1 + (PH) * S1_STAGE; \
       _Pragma("unroll") for (int r = 0; r < RY; ++r) { \
         const V c = CEN[r]; \
-        T wv = __shfl_up_sync(0xffffffffu, v2::Last(c), 1); \
-        T ev = __shfl_down_sync(0xffffffffu, v2::First(c), 1); \
-        if (need_w) wv = *reinterpret_cast<const T *>(cb + r * ROWB + w_in); \
-        if (need_e) ev = *reinterpret_cast<const T *>(cb + r * ROWB + e_in); \
+        const T wv = *reinterpret_cast<const T *>(cb + r * ROWB + w_in); \
+        const T ev = *reinterpret_cast<const T *>(cb + r * ROWB + e_in); \
         const V nv = (r == 0) ? north : CEN[r > 0 ? r - 1 : 0]; \
         const V sv = (r == RY - 1) ? south : CEN[r < RY - 1 ? r + 1 : r]; \
         T1[r] = v2::Vec7<FP>(a, c, wv, ev, sv, nv, BOT[r], TOP[r]); \
@@ -230,10 +228,8 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       } \
       _Pragma("unroll") for (int r = 0; r < RY; ++r) { \
         const V c = C1[r]; \
-        T wv = __shfl_up_sync(0xffffffffu, v2::Last(c), 1); \
-        T ev = __shfl_down_sync(0xffffffffu, v2::First(c), 1); \
-        if (need_w) wv = *reinterpret_cast<const T *>(cb + r * ROWB + w_in); \
-        if (need_e) ev = *reinterpret_cast<const T *>(cb + r * ROWB + e_in); \
+        const T wv = *reinterpret_cast<const T *>(cb + r * ROWB + w_in); \
+        const T ev = *reinterpret_cast<const T *>(cb + r * ROWB + e_in); \
         const V nv = (r == 0) ? north : C1[r > 0 ? r - 1 : 0]; \
         const V sv = (r == RY - 1) ? south : C1[r < RY - 1 ? r + 1 : r]; \
         const V bv = *reinterpret_cast<const V *>(bb + r * ROWB); \
