@@ -82,6 +82,54 @@ __device__ __forceinline__ double2 Vec7(const A &a, double2 c, double wv, double
   return o;
 }
 
+// ---- equal neighbour coefficients (cw == ce == cs == cn == cb == ct =: c6, bit for bit) ----
+// The product c6*v of a value v is then the same number wherever v is a neighbour, so a
+// sweep can form it once per point and reuse it for all six roles: 2 multiplies per point
+// (cc*v and c6*v) instead of 7.  The additions keep the reference's order, so the result
+// is still bit-identical.  Scale() forms the products of a vector, Sum7() adds them up:
+//   q = cc*c, wP / eP = products of the x neighbours of the vector's ends, pc = c6*c (its
+//   elements are the x neighbours of each other), ps / pn / pb / pt = products of the s, n,
+//   b, t vectors.
+__device__ __forceinline__ float4 Scale(float k, const float4 &v) {
+  return make_float4(MulRn(k, v.x), MulRn(k, v.y), MulRn(k, v.z), MulRn(k, v.w));
+}
+__device__ __forceinline__ double2 Scale(double k, const double2 &v) {
+  return make_double2(MulRn(k, v.x), MulRn(k, v.y));
+}
+template <int FP>
+__device__ __forceinline__ float4 Sum7(float4 q, float wP, float eP, float4 pc, float4 ps,
+                                       float4 pn, float4 pb, float4 pt) {
+  // ((q + w) + e): the x terms pair up across vector elements, so they stay scalar
+  const float r0 = AddRn(AddRn(q.x, wP), pc.y);
+  const float r1 = AddRn(AddRn(q.y, pc.x), pc.z);
+  const float r2 = AddRn(AddRn(q.z, pc.y), pc.w);
+  const float r3 = AddRn(AddRn(q.w, pc.z), eP);
+  float4 o;
+  if (FP == 0) {
+    o.x = AddRn(AddRn(AddRn(AddRn(r0, ps.x), pn.x), pb.x), pt.x);
+    o.y = AddRn(AddRn(AddRn(AddRn(r1, ps.y), pn.y), pb.y), pt.y);
+    o.z = AddRn(AddRn(AddRn(AddRn(r2, ps.z), pn.z), pb.z), pt.z);
+    o.w = AddRn(AddRn(AddRn(AddRn(r3, ps.w), pn.w), pb.w), pt.w);
+  } else {
+    u64 r01 = Pack(r0, r1), r23 = Pack(r2, r3);
+    r01 = Add2(r01, Pack(ps.x, ps.y)); r23 = Add2(r23, Pack(ps.z, ps.w));
+    r01 = Add2(r01, Pack(pn.x, pn.y)); r23 = Add2(r23, Pack(pn.z, pn.w));
+    r01 = Add2(r01, Pack(pb.x, pb.y)); r23 = Add2(r23, Pack(pb.z, pb.w));
+    r01 = Add2(r01, Pack(pt.x, pt.y)); r23 = Add2(r23, Pack(pt.z, pt.w));
+    Unpack(r01, o.x, o.y);
+    Unpack(r23, o.z, o.w);
+  }
+  return o;
+}
+template <int FP>
+__device__ __forceinline__ double2 Sum7(double2 q, double wP, double eP, double2 pc, double2 ps,
+                                        double2 pn, double2 pb, double2 pt) {
+  double2 o;
+  o.x = AddRn(AddRn(AddRn(AddRn(AddRn(AddRn(q.x, wP), pc.y), ps.x), pn.x), pb.x), pt.x);
+  o.y = AddRn(AddRn(AddRn(AddRn(AddRn(AddRn(q.y, pc.x), eP), ps.y), pn.y), pb.y), pt.y);
+  return o;
+}
+
 __device__ __forceinline__ float First(const float4 &v) { return v.x; }
 __device__ __forceinline__ float Last(const float4 &v) { return v.w; }
 __device__ __forceinline__ double First(const double2 &v) { return v.x; }

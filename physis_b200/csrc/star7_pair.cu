@@ -84,7 +84,9 @@ struct PairGeom {
 };
 
 // SLAB: the z-slab form (halo planes stored to the ring neighbours, ordering with them)
-template <typename T, int NBX, int NWY, int RY, int MINB, int FP, bool SLAB>
+// ISO: the six neighbour coefficients are equal; the register planes then hold the
+// products c6*value instead of the values (star7_math.cuh), 2 multiplies per point
+template <typename T, int NBX, int NWY, int RY, int MINB, int FP, bool SLAB, bool ISO>
 __global__ void __launch_bounds__(NBX * NWY * 32, MINB)
 Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PairArgs<T> a) {
   using G = Geom<T>;
@@ -141,6 +143,14 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   // One scalar load per side, no shuffles, no predicates.
   const int w_in = x_first ? 0 : rd_west ? -IN_BOX + WEST_EL : -(int)sizeof(T);
   const int e_in = x_last ? (VEC - 1) * (int)sizeof(T) : rd_east ? IN_BOX + EAST_EL : VEC * (int)sizeof(T);
+  const T c6 = a.cw;
+  // ISO form: the raw x neighbours travel between lanes by shuffle (its shared-memory
+  // pipe is the busier one), only the lanes at a box edge load.  The offsets are made
+  // opaque so that they stay in registers instead of being recomputed under a branch.
+  const bool need_w = (lane == 0);
+  const bool need_e = x_last || rd_east;
+  int w_edge = w_in, e_edge = e_in;
+  if (ISO) asm volatile("" : "+r"(w_edge), "+r"(e_edge));
 
   uint32_t par = 0;  // bit s: phase parity of input slot s
   int pstage = 0;                          // issuer: slot the next plane is loaded into
@@ -148,6 +158,11 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #define SP_LOAD(DST, SLOT) do { \
     const unsigned char *p__ = my_in + (SLOT) * IN_STAGE; \
     _Pragma("unroll") for (int r = 0; r < RY; ++r) DST[r] = *reinterpret_cast<const V *>(p__ + r * ROWB); \
+  } while (0)
+#define SP_LOAD_SCALED(DST, SLOT) do { \
+    const unsigned char *p__ = my_in + (SLOT) * IN_STAGE; \
+    _Pragma("unroll") for (int r = 0; r < RY; ++r) \
+      DST[r] = v2::Scale(c6, *reinterpret_cast<const V *>(p__ + r * ROWB)); \
   } while (0)
 #define SP_WAIT(SLOT) do { \
     tma::mbar_wait(&full[(SLOT)], (par >> (SLOT)) & 1u); \
@@ -255,6 +270,84 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     } \
   } while (0)
 
+#define SP_STEP_ISO(PH, BOT, CEN, TOP, C1, T1) do { \
+    SP_WAIT(((PH) + 2) % 3); \
+    SP_LOAD_SCALED(TOP, ((PH) + 2) % 3); \
+    SP_YFIX(TOP); \
+    { \
+      const unsigned char *cb = my_in + (((PH) + 1) % 3) * IN_STAGE; \
+      V north = v2::Scale(c6, *reinterpret_cast<const V *>(cb - ROWB)); \
+      V south = v2::Scale(c6, *reinterpret_cast<const V *>(cb + RY * ROWB)); \
+      SP_YFIX_NS(north, south, CEN); \
+      unsigned char *sp = my_s1 + (PH) * S1_STAGE; \
+      _Pragma("unroll") for (int r = 0; r < RY; ++r) { \
+        const V pc = CEN[r]; \
+        const V c = *reinterpret_cast<const V *>(cb + r * ROWB); \
+        const V q = v2::Scale(a.cc, c); \
+        T wv = __shfl_up_sync(0xffffffffu, v2::Last(c), 1); \
+        T ev = __shfl_down_sync(0xffffffffu, v2::First(c), 1); \
+        if (need_w) wv = *reinterpret_cast<const T *>(cb + r * ROWB + w_edge); \
+        if (need_e) ev = *reinterpret_cast<const T *>(cb + r * ROWB + e_edge); \
+        const T wP = MulRn(c6, wv), eP = MulRn(c6, ev); \
+        const V nv = (r == 0) ? north : CEN[r > 0 ? r - 1 : 0]; \
+        const V sv = (r == RY - 1) ? south : CEN[r < RY - 1 ? r + 1 : r]; \
+        const V s1v = v2::Sum7<FP>(q, wP, eP, pc, sv, nv, BOT[r], TOP[r]); \
+        *reinterpret_cast<V *>(sp + r * ROWB) = s1v; \
+        T1[r] = v2::Scale(c6, s1v); \
+      } \
+      SP_YFIX(T1); \
+    } \
+    __syncthreads(); \
+    if (issuer) { \
+      /* thread 0 owns tile row 0: the box starts one row above it */ \
+      if (k == k0 && k + 3 <= ze + 1) SP_ISSUE(ybase - 1, k + 3); \
+      if (k + 4 <= ze + 1) SP_ISSUE(ybase - 1, k + 4); \
+    } \
+    if (k >= zb) { \
+      const unsigned char *cb = my_s1 + (((PH) + 2) % 3) * S1_STAGE; \
+      /* bottom plane: s1 plane k-1, or (z face) the centre plane itself */ \
+      const unsigned char *bb = (k == a.zface_lo) ? cb : my_s1 + (((PH) + 1) % 3) * S1_STAGE; \
+      V north = v2::Scale(c6, *reinterpret_cast<const V *>(cb - ROWB)); \
+      V south = v2::Scale(c6, *reinterpret_cast<const V *>(cb + RY * ROWB)); \
+      SP_YFIX_NS(north, south, C1); \
+      /* top plane beyond the z face: the centre plane (rare: a loop keeps it a branch) */ \
+      for (int e__ = (k == a.zface_hi) ? 1 : 0; e__ > 0; --e__) { \
+        _Pragma("unroll") for (int r = 0; r < RY; ++r) T1[r] = C1[r]; \
+      } \
+      _Pragma("unroll") for (int r = 0; r < RY; ++r) { \
+        const V pc = C1[r]; \
+        const V c = *reinterpret_cast<const V *>(cb + r * ROWB); \
+        const V q = v2::Scale(a.cc, c); \
+        T wv = __shfl_up_sync(0xffffffffu, v2::Last(c), 1); \
+        T ev = __shfl_down_sync(0xffffffffu, v2::First(c), 1); \
+        if (need_w) wv = *reinterpret_cast<const T *>(cb + r * ROWB + w_edge); \
+        if (need_e) ev = *reinterpret_cast<const T *>(cb + r * ROWB + e_edge); \
+        const T wP = MulRn(c6, wv), eP = MulRn(c6, ev); \
+        const V nv = (r == 0) ? north : C1[r > 0 ? r - 1 : 0]; \
+        const V sv = (r == RY - 1) ? south : C1[r < RY - 1 ? r + 1 : r]; \
+        const V bv = v2::Scale(c6, *reinterpret_cast<const V *>(bb + r * ROWB)); \
+        const V o = v2::Sum7<FP>(q, wP, eP, pc, sv, nv, bv, T1[r]); \
+        if (st_ok[r]) StoreVec(reinterpret_cast<V *>(obase + (size_t)r * a.nx), o, a.st_hint != 0); \
+      } \
+      if (SLAB) { \
+        /* the slab's first two / last two planes also go to the ring neighbours' halos: each \
+           thread forwards the vectors it has just stored (a rare path kept out of the row \
+           loop; a thread reading back its own stores needs no fence) */ \
+        const long long pushd = ((unsigned)(k - a.push_lo_z) < 2u) ? a.push_lo_delta \
+                              : ((unsigned)(k - a.push_hi_z) < 2u) ? a.push_hi_delta : 0ll; \
+        for (int e__ = pushd ? 1 : 0; e__ > 0; --e__) { \
+          _Pragma("unroll") for (int r = 0; r < RY; ++r) { \
+            if (st_ok[r]) { \
+              V *src__ = reinterpret_cast<V *>(obase + (size_t)r * a.nx); \
+              *reinterpret_cast<V *>(reinterpret_cast<char *>(src__) + pushd) = *src__; \
+            } \
+          } \
+        } \
+      } \
+      obase += plane_elems; \
+    } \
+  } while (0)
+
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
     const int zci = item / a.nty;
     const int ty = item - zci * a.nty;
@@ -285,26 +378,39 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     V w0[RY], w1[RY], w2[RY];  // input window (own cells); roles rotate, registers do not move
     V q0[RY], q1[RY], q2[RY];  // first-sweep planes (own cells); two of the three are live
     SP_WAIT(0);
-    SP_LOAD(w0, 0);
+    if (ISO) SP_LOAD_SCALED(w0, 0); else SP_LOAD(w0, 0);
     SP_YFIX(w0);
     SP_WAIT(1);
-    SP_LOAD(w1, 1);
+    if (ISO) SP_LOAD_SCALED(w1, 1); else SP_LOAD(w1, 1);
     SP_YFIX(w1);
 #pragma unroll
     for (int r = 0; r < RY; ++r) q2[r] = w1[r];  // defined value; selected by no store
 
     int k = k0;
-    for (;;) {
-      SP_STEP(0, w0, w1, w2, q2, q0);
-      if (++k >= ze) break;
-      SP_STEP(1, w1, w2, w0, q0, q1);
-      if (++k >= ze) break;
-      SP_STEP(2, w2, w0, w1, q1, q2);
-      if (++k >= ze) break;
+    if (ISO) {
+      for (;;) {
+        SP_STEP_ISO(0, w0, w1, w2, q2, q0);
+        if (++k >= ze) break;
+        SP_STEP_ISO(1, w1, w2, w0, q0, q1);
+        if (++k >= ze) break;
+        SP_STEP_ISO(2, w2, w0, w1, q1, q2);
+        if (++k >= ze) break;
+      }
+    } else {
+      for (;;) {
+        SP_STEP(0, w0, w1, w2, q2, q0);
+        if (++k >= ze) break;
+        SP_STEP(1, w1, w2, w0, q0, q1);
+        if (++k >= ze) break;
+        SP_STEP(2, w2, w0, w1, q1, q2);
+        if (++k >= ze) break;
+      }
     }
   }
   if (SLAB) SlabSyncSignal(a.sync, PG::THREADS, threadIdx.x == 0);
 #undef SP_STEP
+#undef SP_STEP_ISO
+#undef SP_LOAD_SCALED
 #undef SP_YFIX_NS
 #undef SP_YFIX
 #undef SP_ISSUE
@@ -318,17 +424,25 @@ struct PairVariant {
   int nbx, nwy, ry, minb;
   const void *f32[2][2];  // [one GPU / z-slab][scalar / packed-add arithmetic]
   const void *f64[2];
+  const void *f32_iso[2][2];  // equal neighbour coefficients
+  const void *f64_iso[2];
   int smem_f32, smem_f64, threads;
 };
 
 #define PAIR_VARIANT(NBX, NWY, RY, MINB) \
   { NBX, NWY, RY, MINB, \
-    {{(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0, false>, \
-      (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, false>}, \
-     {(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0, true>, \
-      (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, true>}}, \
-    {(const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, false>, \
-     (const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, true>}, \
+    {{(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0, false, false>, \
+      (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, false, false>}, \
+     {(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0, true, false>, \
+      (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, true, false>}}, \
+    {(const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, false, false>, \
+     (const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, true, false>}, \
+    {{(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0, false, true>, \
+      (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, false, true>}, \
+     {(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0, true, true>, \
+      (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, true, true>}}, \
+    {(const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, false, true>, \
+     (const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, true, true>}, \
     PairGeom<float, NBX, NWY, RY>::SMEM, PairGeom<double, NBX, NWY, RY>::SMEM, NBX * NWY * 32 }
 
 const PairVariant kPairVariants[] = {
@@ -343,6 +457,7 @@ constexpr int kNumPairVariants = sizeof(kPairVariants) / sizeof(kPairVariants[0]
 
 struct Star7PairPlan {
   bool is_double = false;
+  bool iso = false;
   int grid = 0, block = 0;
   size_t smem = 0;
   const void *fn = nullptr;
@@ -412,7 +527,16 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
 
   Star7PairPlan *p = new Star7PairPlan();
   p->is_double = dbl;
-  p->fn = dbl ? v.f64[multi ? 1 : 0] : v.f32[multi ? 1 : 0][o.star7_impl == 2 ? 1 : 0];
+  // equal neighbour coefficients (the benchmark's isotropic case): 2 multiplies per point
+  bool iso = o.star7_iso != 0;
+  for (int i = 1; i < 6 && iso; ++i) {
+    if (dbl) iso = (d0.scalars[i] == d0.scalars[0]);
+    else iso = ((float)d0.scalars[i] == (float)d0.scalars[0]);
+  }
+  const int ms = multi ? 1 : 0, fp = o.star7_impl == 2 ? 1 : 0;
+  if (iso) p->fn = dbl ? v.f64_iso[ms] : v.f32_iso[ms][fp];
+  else p->fn = dbl ? v.f64[ms] : v.f32[ms][fp];
+  p->iso = iso;
   p->smem = dbl ? v.smem_f64 : v.smem_f32;
   p->block = v.threads;
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));

@@ -39,10 +39,12 @@ def case_pair():
     from physis_b200 import api
     co64 = np.array([0.11, 0.07, 0.13, 0.05, 0.17, 0.03, 0.44])
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cases = [((128, 32, 16), 3, np.float32, ()), ((256, 20, 33), 5, np.float32, ("star7_pair_zc=3",)),
-             ((512, 17, 24), 4, np.float32, ()), ((64, 30, 19), 6, np.float64, ("star7_pair_zc=2",)),
-             ((384, 9, 41), 3, np.float32, ("star7_impl=1",))]
-    for shape, iters, dtype, opts in cases:
+    iso64 = np.array([0.1234567] * 6 + [0.2592598])   # equal neighbour coefficients: shared-product form
+    cases = [((128, 32, 16), 3, np.float32, (), co64), ((256, 20, 33), 5, np.float32, ("star7_pair_zc=3",), co64),
+             ((512, 17, 24), 4, np.float32, (), iso64), ((64, 30, 19), 6, np.float64, ("star7_pair_zc=2",), co64),
+             ((384, 9, 41), 3, np.float32, ("star7_impl=1",), co64), ((128, 21, 26), 5, np.float64, (), iso64),
+             ((256, 12, 35), 4, np.float32, ("star7_pair_zc=6",), iso64)]
+    for shape, iters, dtype, opts, co64 in cases:
         nx, ny, nz = shape
         api.PSInit(["t"], 3, shape)
         for kv in opts:

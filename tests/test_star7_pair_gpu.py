@@ -12,9 +12,11 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 CO = np.array([0.11, 0.07, 0.13, 0.05, 0.17, 0.03, 0.44])  # ce, cw, cn, cs, ct, cb, cc
+# equal neighbour coefficients (the benchmark's isotropic case) select the shared-product form
+CO_ISO = np.array([0.1234567] * 6 + [0.2592598])
 
 
-def _run_pair(shape, iters, dtype, options=()):
+def _run_pair(shape, iters, dtype, options=(), coeffs=None):
     """PSStencilRun(map(A->B), map(B->A), iters) through the C ABI; returns (A, B, stats)."""
     from physis_b200 import api
     nx, ny, nz = shape
@@ -30,7 +32,7 @@ def _run_pair(shape, iters, dtype, options=()):
         a.copyin(f0)
         b.copyin(g0)
         dom = api.PSDomain3DNew(0, nx, 0, ny, 0, nz)
-        co = [float(dtype(c)) for c in CO]
+        co = [float(dtype(c)) for c in (CO if coeffs is None else coeffs)]
         d0 = api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, dom, [a, b], co, elm_type=pt)
         d1 = api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, dom, [b, a], co, elm_type=pt)
         api.rt().__PSB200ResetStats()
@@ -105,3 +107,26 @@ def test_unfused_schedule_unchanged():
     assert pairs == 0 and launches == 6
     want = H.diffusion7_numpy(f0, (1024, 12, 6), CO.astype(np.float32), 6)
     assert np.array_equal(fa.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,iters,opts", [
+    ((512, 40, 24), 3, ()),
+    ((256, 33, 19), 4, ("star7_pair_zc=5",)),
+    ((128, 30, 17), 5, ("star7_pair_zc=4",)),
+    ((200, 29, 9), 3, ("star7_pair_zc=1",)),
+    ((64, 5, 6), 4, ()),
+    ((256, 15, 33), 7, ("star7_impl=1", "star7_pair_zc=8")),
+    ((256, 47, 20), 3, ("star7_iso=0",)),
+])
+def test_fused_pair_equal_coefficients(shape, iters, opts, dtype):
+    if dtype == np.float64:
+        shape = (shape[0] // 2, shape[1], shape[2])
+    f0, fa, fb, launches, pairs = _run_pair(shape, iters, dtype, opts, coeffs=CO_ISO)
+    assert pairs == ((iters - 1) & ~1) and pairs > 0, "the fused pass did not run"
+    co = CO_ISO.astype(dtype)
+    view = np.uint32 if dtype == np.float32 else np.uint64
+    want_a = H.diffusion7_numpy(f0, shape, co, 2 * iters)
+    want_b = H.diffusion7_numpy(f0, shape, co, 2 * iters - 1)
+    assert np.array_equal(fa.view(view), want_a.view(view))
+    assert np.array_equal(fb.view(view), want_b.view(view))
