@@ -150,18 +150,9 @@ def _barrier(dist):
 
 # ------------------------------------------------------------------ reference arm
 
-def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path (REFERENCE target) on host cores."""
-    if rank != 0:
-        return
+def _ref_target_glups(lib, n, sweeps, reps=1, warm=0):
+    """The Physis REFERENCE target (libphysis_rt_ref + translator-shaped sweep): sequential code."""
     import helpers as H
-    lib = H.oracle_ref()
-    kind = "reference"
-    if lib is None:
-        lib = H.oracle_port()
-        kind = "port"
-    n = args.size
-    sweeps = 2  # bounded sample: ~1 s per 512^3 sweep on one core
     p = H.diffusion_params(n, n, n)
     f0 = H.diffusion_initial(n, n, n, p)
     lib.initialize_physis.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -171,24 +162,78 @@ def run_reference(args, rank, world):
     lib.copyin_physis(f0.ctypes.data)
     lib.run_sweeps_only_physis.argtypes = [C.c_int] * 4 + [C.c_float] * 7
     co = [float(c) for c in p[:7]]
-    for _ in range(args.warmup):
+    for _ in range(warm):
         lib.run_sweeps_only_physis(sweeps, n, n, n, *co)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(reps):
         lib.run_sweeps_only_physis(sweeps, n, n, n, *co)
     dt = time.perf_counter() - t0
     lib.finalize_benchmark_physis()
-    glups = n ** 3 * sweeps * args.steps / dt / 1e9
-    sample = f"{sweeps} sweeps of {n}^3 per step, REFERENCE target (sequential codegen), 1 thread"
+    return n ** 3 * sweeps * reps / dt / 1e9, dt
+
+
+def _ref_openmp_glups(lib, n, sweeps, reps=1, warm=0):
+    """The reference's own multi-threaded CPU form of the same sweep
+    (examples/diffusion-benchmark/diffusion3d_openmp.cc, unmodified, all host threads)."""
+    import helpers as H
+    p = H.diffusion_params(n, n, n)
+    f0 = H.diffusion_initial(n, n, n, p)
+    lib.ref_openmp_load.argtypes = [C.c_int] * 3 + [C.c_void_p]
+    lib.ref_openmp_store.argtypes = [C.c_void_p]
+    try:  # launchers (torchrun) pin OMP_NUM_THREADS=1; this arm is meant to use every host core
+        C.CDLL("libgomp.so.1").omp_set_num_threads(os.cpu_count() or 1)
+    except OSError:
+        pass
+    lib.ref_openmp_load(n, n, n, f0.ctypes.data)
+    for _ in range(warm):
+        lib.ref_openmp_sweeps(sweeps)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        lib.ref_openmp_sweeps(sweeps)
+    dt = time.perf_counter() - t0
+    lib.ref_openmp_store(f0.ctypes.data)
+    return n ** 3 * sweeps * reps / dt / 1e9, dt, int(lib.ref_openmp_threads())
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path on the box's host cores: its OpenMP
+    form of the sweep on all host threads (the headline of this arm), with the Physis
+    REFERENCE target (sequential by construction, translator/reference_runtime_builder.cc:605-664)
+    beside it.  Falls back to the oracle port (1 thread) where oracle/_ref was never built."""
+    if rank != 0:
+        return
+    import helpers as H
+    n = args.size
+    lib = H.oracle_ref()
+    extra = {}
+    if lib is not None:
+        sweeps = 20   # bounded sample: ~0.1 s per 512^3 sweep on 16 cores
+        glups, dt, threads = _ref_openmp_glups(lib, n, sweeps, reps=max(args.steps, 1), warm=args.warmup)
+        kind, cores = "reference", threads
+        sample = (f"{sweeps} sweeps of {n}^3 per step, the reference's diffusion3d_openmp.cc "
+                  f"on {threads} host threads")
+        ms_per_step = dt / max(args.steps, 1) * 1e3
+        g1, _ = _ref_target_glups(lib, min(n, 256), 4)
+        extra["ref_target_1thread"] = {"value": g1, "unit": "GLUP/s", "cores": 1,
+                                       "sample": f"4 sweeps of {min(n, 256)}^3, Physis REFERENCE target"}
+    else:
+        lib = H.oracle_port()
+        sweeps = 2
+        glups, dt = _ref_target_glups(lib, n, sweeps, reps=max(args.steps, 1), warm=args.warmup)
+        kind, cores = "port", 1
+        sample = f"{sweeps} sweeps of {n}^3 per step, CPU restatement of the REFERENCE target, 1 thread"
+        ms_per_step = dt / max(args.steps, 1) * 1e3
+    cpu = {"value": glups, "unit": "GLUP/s", "cores": cores, "kind": kind, "sample": sample,
+           "host_cores": os.cpu_count()}
+    cpu.update(extra)
     line = {
         "impl": "reference", "metric": "7-pt diffusion GLUP/s", "value": glups, "unit": "GLUP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"7-pt 3D diffusion fp32 {n}^3 (BASELINE config 2 shape), "
                                f"bounded sample of {sweeps} sweeps/step on host CPU"},
-        "cpu_baseline": {"value": glups, "unit": "GLUP/s", "cores": 1, "kind": kind,
-                         "sample": sample, "host_cores": os.cpu_count()},
+        "cpu_baseline": cpu,
         "e2e": {"value": glups, "unit": "GLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     _emit(line)
@@ -197,29 +242,27 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------ b200 arm
 
 def cpu_baseline_sample():
-    """Config 1 (256^3, 100 sweeps) on one host core through the reference's REF runtime."""
+    """Config 1 (256^3, 100 sweeps) on the host cores: the reference's OpenMP form on all
+    threads and the Physis REFERENCE target on one (its codegen is sequential)."""
     import helpers as H
-    lib = H.oracle_ref()
-    kind = "reference"
-    if lib is None:
-        lib, kind = H.oracle_port(), "port"
     n, sweeps = 256, 100
-    p = H.diffusion_params(n, n, n)
-    f0 = H.diffusion_initial(n, n, n, p)
-    lib.initialize_physis.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
-    lib.initialize_physis(0, None, n, n, n)
-    lib.initialize_benchmark_physis(n, n, n)
-    lib.copyin_physis.argtypes = [C.c_void_p]
-    lib.copyin_physis(f0.ctypes.data)
-    lib.run_sweeps_only_physis.argtypes = [C.c_int] * 4 + [C.c_float] * 7
-    t0 = time.perf_counter()
-    lib.run_sweeps_only_physis(sweeps, n, n, n, *[float(c) for c in p[:7]])
-    dt = time.perf_counter() - t0
-    lib.finalize_benchmark_physis()
-    return {"value": n ** 3 * sweeps / dt / 1e9, "unit": "GLUP/s", "cores": 1, "kind": kind,
-            "host_cores": os.cpu_count(), "seconds": dt,
-            "sample": f"BASELINE config 1: {n}^3 fp32, {sweeps} sweeps, REFERENCE target "
-                      "(libphysis_rt_ref + translator-shaped sweep), 1 thread (REF codegen is sequential)"}
+    lib = H.oracle_ref()
+    if lib is None:
+        glups, dt = _ref_target_glups(H.oracle_port(), n, sweeps)
+        return {"value": glups, "unit": "GLUP/s", "cores": 1, "kind": "port",
+                "host_cores": os.cpu_count(), "seconds": dt,
+                "sample": f"BASELINE config 1: {n}^3 fp32, {sweeps} sweeps, CPU restatement of the "
+                          "REFERENCE target, 1 thread"}
+    g1, dt1 = _ref_target_glups(lib, n, sweeps)
+    gomp, dto, threads = _ref_openmp_glups(lib, n, sweeps, reps=3, warm=1)
+    return {"value": gomp, "unit": "GLUP/s", "cores": threads, "kind": "reference",
+            "host_cores": os.cpu_count(), "seconds": dt1 + dto,
+            "sample": f"BASELINE config 1: {n}^3 fp32, {sweeps} sweeps x3, the reference's "
+                      f"diffusion3d_openmp.cc on {threads} host threads",
+            "ref_target_1thread": {"value": g1, "unit": "GLUP/s", "cores": 1, "seconds": dt1,
+                                   "sample": f"{n}^3 fp32, {sweeps} sweeps, Physis REFERENCE target "
+                                             "(libphysis_rt_ref + translator-shaped sweep; REF codegen "
+                                             "is sequential)"}}
 
 
 def himeno_line(args, api, lib, world, dist):

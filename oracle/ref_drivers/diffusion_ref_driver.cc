@@ -4,6 +4,8 @@
 // oracle/_ref/ (see oracle/Makefile).  Nothing here restates an algorithm; it
 // only exposes the reference's protected members to ctypes.
 #include "baseline.h"
+#include "diffusion3d_openmp.h"
+#include <omp.h>
 #include <string.h>
 
 namespace {
@@ -37,9 +39,35 @@ class BaselineProbe : public diffusion3d::Baseline {
     free(f);
   }
 };
+// The reference's OpenMP form of the sweep (diffusion3d_openmp.cc), on a caller-provided field.
+class OpenMPProbe : public diffusion3d::Diffusion3DOpenMP {
+ public:
+  OpenMPProbe(int nx, int ny, int nz) : diffusion3d::Diffusion3DOpenMP(nx, ny, nz) {}
+  void Load(const float *field) {
+    InitializeBenchmark();
+    memcpy(f1_, field, sizeof(float) * (size_t)nx_ * ny_ * nz_);
+  }
+  void Sweeps(int count) { RunKernel(count); }
+  void Store(float *field) {
+    memcpy(field, f1_, sizeof(float) * (size_t)nx_ * ny_ * nz_);
+    FinalizeBenchmark();
+  }
+};
+OpenMPProbe *g_omp = nullptr;
 }  // namespace
 
 extern "C" {
+int ref_openmp_threads(void) { return omp_get_max_threads(); }
+void ref_openmp_load(int nx, int ny, int nz, const float *field) {
+  g_omp = new OpenMPProbe(nx, ny, nz);
+  g_omp->Load(field);
+}
+void ref_openmp_sweeps(int count) { g_omp->Sweeps(count); }
+void ref_openmp_store(float *field) {
+  g_omp->Store(field);
+  delete g_omp;
+  g_omp = nullptr;
+}
 void ref_diffusion3d_params(int nx, int ny, int nz, float *out) {
   BaselineProbe b(nx, ny, nz);
   b.Params(out);

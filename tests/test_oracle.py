@@ -207,3 +207,23 @@ def test_numpy_restatement_equals_c_oracle(shape, count):
     want = H.run_diffusion(H.oracle_port(), f0, nx, ny, nz, count, co)
     got = H.diffusion7_numpy(f0, shape, co, count)
     assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+
+
+def test_reference_openmp_form_equals_oracle():
+    """The reference's own multi-threaded CPU form of the sweep (diffusion3d_openmp.cc, built
+    unmodified into oracle/_ref and timed by bench.py's reference arm) computes the same bits
+    as the oracle."""
+    ref = H.oracle_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref was never built (needs /root/reference)")
+    nx, ny, nz, count = 48, 20, 13, 6
+    p = H.diffusion_params(nx, ny, nz)
+    f0 = H.diffusion_initial(nx, ny, nz, p)
+    want = H.run_diffusion(H.oracle_port(), f0, nx, ny, nz, count, p)
+    got = f0.copy()
+    ref.ref_openmp_load.argtypes = [C.c_int] * 3 + [C.c_void_p]
+    ref.ref_openmp_store.argtypes = [C.c_void_p]
+    ref.ref_openmp_load(nx, ny, nz, got.ctypes.data)
+    ref.ref_openmp_sweeps(count)
+    ref.ref_openmp_store(got.ctypes.data)
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
