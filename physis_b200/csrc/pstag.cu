@@ -19,9 +19,14 @@
 // plus the periodic wrap done by the producer: the tile's interior rows, its
 // two y-halo rows and (for tiles touching x=0 / x=nx-1) a 16-byte-wide wrap
 // column are separate TMA boxes, and z wraps in the plane coordinate.  kap's row
-// pitch ((N+1)*8 bytes) is not a multiple of 16, so it cannot be a TMA tensor;
-// it is read with coalesced 8-byte loads (each value reused from L1 by the 8
-// cells around it) and carried from plane z+1 to z in registers.
+// pitch ((N+1)*8 bytes) is not a multiple of 16, so it cannot be a 3-D TMA tensor;
+// it is described as a FLAT 1-D tensor instead and every row segment of a tile's
+// (TY+1) x (TXB+1) vertex patch is one 1-D TMA box into the same ring stage as the
+// p plane.  A box must start on a 16-byte boundary (measured: an odd fp64 start
+// element raises an illegal-instruction error), so each row is fetched from the even
+// element at or before its first vertex and the consumers add the row's parity when
+// they read.  Each thread takes its 3 x (RY+1) values with 8-byte shared-memory loads
+// and carries plane z+1 to z in registers.
 #include "runtime.h"
 #include "tma.cuh"
 #include "sweep_common.cuh"
@@ -37,9 +42,8 @@ using namespace sweep;
 
 struct PstagArgs {
   double *out;
-  const double *kap;
   int nx, ny, nz;     // cell grid
-  int kx, ky;         // kap pitches (nx+1, ny+1)
+  int kx, ky, kz;     // kap extents (nx+1, ny+1, local planes)
   int dx0, dx1, dy0, dy1, dz0, dz1;
   int ntx, nty, nzc, zc, nitems;
   int stages;
@@ -64,7 +68,11 @@ struct PstagLayout {
   static constexpr int SOUTH = NORTH + Up128(ROWB);
   static constexpr int WEST = SOUTH + Up128(ROWB);
   static constexpr int EAST = WEST + Up128(TY * 16);
-  static constexpr int STRIDE = EAST + Up128(TY * 16);
+  // kap patch: TY+1 rows of TXB+2 vertices (TXB+1 used; the box must be a multiple of 16 bytes)
+  static constexpr int KAP = EAST + Up128(TY * 16);
+  static constexpr int KBOX = Geom<double>::TXB + 4;  // TXB+1 vertices, +1 for an odd start, 16-byte multiple
+  static constexpr int KROW = Up128(KBOX * 8);
+  static constexpr int STRIDE = KAP + (TY + 1) * KROW;
 };
 template <int TY>
 constexpr int PstagBoxStride() { return PstagLayout<TY>::STRIDE; }
@@ -72,7 +80,8 @@ constexpr int PstagBoxStride() { return PstagLayout<TY>::STRIDE; }
 template <int TY, int RY, int NBX, int MINB>
 __global__ void __launch_bounds__((NBX * (TY / RY) + 1) * 32, MINB)
 PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant__ CUtensorMap map_row,
-            const __grid_constant__ CUtensorMap map_col, const __grid_constant__ PstagArgs a) {
+            const __grid_constant__ CUtensorMap map_col, const __grid_constant__ CUtensorMap map_kap,
+            const __grid_constant__ PstagArgs a) {
   using G = Geom<double>;
   constexpr int VEC = 2;
   constexpr int NWY = TY / RY;
@@ -81,8 +90,7 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
   using L = PstagLayout<TY>;
   constexpr int BOX_STRIDE = L::STRIDE;
   constexpr int STAGE_BYTES = NBX * BOX_STRIDE;
-  constexpr int NT = NW * 32;   // consumer threads
-  constexpr int KD = 3;         // kap slots: plane z+1 in use, z+2 and z+3 in flight (z+3 reuses the slot of z)
+  constexpr int KROW = L::KROW;
 
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -110,6 +118,7 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
     tma::prefetch_tensormap(&map_main);
     tma::prefetch_tensormap(&map_row);
     tma::prefetch_tensormap(&map_col);
+    tma::prefetch_tensormap(&map_kap);
     int stage = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
@@ -128,7 +137,7 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
       for (int b = 0; b < NBX; ++b) {
         const int bx0 = x0 + b * G::TXB;
         if (bx0 >= a.nx) continue;
-        tx_bytes += (uint32_t)((TY + 2) * ROWB);
+        tx_bytes += (uint32_t)((TY + 2) * ROWB) + (uint32_t)((TY + 1) * L::KBOX * 8);
         if (bx0 == 0) tx_bytes += TY * 16;
         if (bx0 + G::TXB >= a.nx) tx_bytes += TY * 16;
       }
@@ -149,6 +158,12 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
             tma::load_3d(bd + L::WEST, &map_col, &full[stage], a.nx - G::HX, y0, z);
           if (bx0 + G::TXB >= a.nx)
             tma::load_3d(bd + L::EAST, &map_col, &full[stage], 0, y0, z);
+          // vertex patch of plane zz (kap does not wrap: it has one more plane than u)
+          const int zk = min(max(zz, 0), a.kz - 1);
+          const int k0 = (zk * a.ky + y0) * a.kx + bx0;
+#pragma unroll
+          for (int rr = 0; rr <= TY; ++rr)
+            tma::load_1d(bd + L::KAP + rr * KROW, &map_kap, &full[stage], (k0 + rr * a.kx) & ~1);
         }
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
@@ -158,9 +173,6 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
 
   const int bx = warp % NBX;
   const int wy = warp / NBX;
-  const int ctid = threadIdx.x;  // consumer thread index (the producer is the last warp)
-  const double *kap_ring = reinterpret_cast<const double *>(planes + S * STAGE_BYTES);
-  const uint32_t kap_smem = tma::smem_u32(kap_ring);
   const int col_off = (G::HX + lane * VEC) * (int)sizeof(double);
   const int row0 = wy * RY;  // first own row inside the MAIN region
   const int north_off = (wy == 0) ? L::NORTH : (row0 - 1) * ROWB;
@@ -196,37 +208,17 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
     // kap values at plane z (lo) and z+1 (hi): rows ybase .. ybase+RY, x .. x+2
     double klo[RY + 1][3], khi[RY + 1][3];
 
-    // kap is staged through shared memory with cp.async, two planes ahead of its use,
-    // so its global-load latency is off the consumers' critical path (its row pitch,
-    // (nx+1)*8 bytes, rules out TMA and 16-byte accesses).  Every thread copies and
-    // reads back only its own 3 x (RY+1) values: [slot][row][element][thread], 8 bytes.
-    const int kz_max = ze;  // last kap plane this item reads
-    auto issue_kap = [&](int z) {
-      const int zc_ = min(z, kz_max);
-      const int slot = z % KD;
+    // this thread's 3 x (RY+1) vertices of the kap plane that arrived in ring stage `st`
+    // (kz = the kap plane: row r of the patch starts at flat element e, fetched from e & ~1)
+    auto load_kap = [&](double (&k)[RY + 1][3], int st, int kz) {
+      const unsigned char *kp = box + st * STAGE_BYTES + L::KAP + row0 * KROW + lane * 16;
+      const int e0 = (kz * a.ky + (ybase - wy * RY) + row0) * a.kx + bx0;
 #pragma unroll
       for (int r = 0; r <= RY; ++r) {
-        const int y = min(ybase + r, a.ky - 1);
-        const double *row = a.kap + ((size_t)zc_ * a.ky + y) * a.kx;
-        const int xx = min(x, a.kx - 2);
-        const uint32_t dst = kap_smem + (uint32_t)(((slot * (RY + 1) + r) * 3) * NT + ctid) * 8u;
-        tma::cp_async8(dst, row + xx);
-        tma::cp_async8(dst + NT * 8u, row + xx + 1);
-        tma::cp_async8(dst + 2u * NT * 8u, row + min(xx + 2, a.kx - 1));
-      }
-      tma::cp_async_commit();
-    };
-    auto load_kap = [&](double (&k)[RY + 1][3], int z) {
-      const int slot = z % KD;
-#pragma unroll
-      for (int r = 0; r <= RY; ++r) {
-        const double *src = kap_ring + (size_t)((slot * (RY + 1) + r) * 3) * NT + ctid;
-        k[r][0] = src[0]; k[r][1] = src[NT]; k[r][2] = src[2 * NT];
+        const double *src = reinterpret_cast<const double *>(kp + r * KROW) + ((e0 + r * a.kx) & 1);
+        k[r][0] = src[0]; k[r][1] = src[1]; k[r][2] = src[2];
       }
     };
-    issue_kap(zb);
-    issue_kap(zb + 1);
-    issue_kap(zb + 2);
 
     // plane zb-1 -> bot
     tma::mbar_wait(&full[stage], phase);
@@ -244,16 +236,13 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
 #pragma unroll
       for (int r = 0; r < RY; ++r) cen[r] = *reinterpret_cast<const double2 *>(p + r * ROWB);
     }
+    load_kap(klo, stage_c, zb);   // kap(zb) came with plane zb
     advance();
-    tma::cp_async_wait<2>();   // kap(zb) has landed
-    load_kap(klo, zb);
 
     for (int z = zb; z < ze; ++z) {
-      issue_kap(z + 3);
-      tma::cp_async_wait<2>();  // kap(z+1) has landed; z+2 and z+3 may be in flight
-      load_kap(khi, z + 1);
       const int stage_t = stage;
       tma::mbar_wait(&full[stage], phase);
+      load_kap(khi, stage_t, z + 1);   // kap(z+1) came with plane z+1
       {
         const unsigned char *p = box + stage * STAGE_BYTES + row0 * ROWB + col_off;
 #pragma unroll
@@ -324,12 +313,9 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
       }
     }
     release(stage_c);
-    tma::cp_async_wait<0>();  // nothing of this item still lands in the kap slots
   }
   SlabSyncSignal(a.sync, NW * 32, threadIdx.x == 0);
 }
-
-constexpr int kKapSlots = 3;
 
 // tile shapes (rows, rows per thread, boxes side by side); selected by option pstag_variant
 struct PstagVariant {
@@ -359,7 +345,7 @@ constexpr int kNumPstagVariants = sizeof(kPstagVariants) / sizeof(kPstagVariants
 struct PstagPlan {
   int grid = 0, block = 0;
   size_t smem = 0;
-  CUtensorMap map_main, map_row, map_col;
+  CUtensorMap map_main, map_row, map_col, map_kap;
   PstagArgs args;
   const void *fn = nullptr;
   bool pushes = false;
@@ -389,7 +375,7 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
     *why = "x extent and domain x-range must be even"; return nullptr;
   }
   int vi = rt->opt.pstag_variant;
-  if (vi < 0 || vi >= kNumPstagVariants) vi = 6;
+  if (vi < 0 || vi >= kNumPstagVariants) vi = 4;
   // the default tile is 8 rows; grids whose y extent is not a multiple of it try 4 rows
   if (ny % kPstagVariants[vi].ty != 0 && ny % 4 == 0) vi = 9;
   const PstagVariant &V = kPstagVariants[vi];
@@ -406,10 +392,9 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   p->fn = V.fn;
   int stages = rt->opt.pstag_stages > 0 ? std::min(rt->opt.pstag_stages, kMaxStages) : 6;
   if (stages < 3) stages = 3;
-  const size_t kap_ring = (size_t)kKapSlots * (kRY + 1) * 3 * (kNBX * (kTY / kRY) * 32) * sizeof(double);
-  while (stages > 3 && kBarrierBytes + (size_t)stages * kNBX * V.box_stride + kap_ring > 227 * 1024)
+  while (stages > 3 && kBarrierBytes + (size_t)stages * kNBX * V.box_stride > 227 * 1024)
     --stages;
-  p->smem = kBarrierBytes + (size_t)stages * kNBX * V.box_stride + kap_ring;
+  p->smem = kBarrierBytes + (size_t)stages * kNBX * V.box_stride;
   p->block = (kNBX * (kTY / kRY) + 1) * 32;
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   int occ = 0;
@@ -420,9 +405,8 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   PstagArgs &a = p->args;
   p->wr_member = wr;
   a.out = (double *)mw.dev;
-  a.kap = (const double *)kap->members[0].dev;
   a.nx = nx; a.ny = ny; a.nz = nz;
-  a.kx = kap->ldim[0]; a.ky = kap->ldim[1];
+  a.kx = kap->ldim[0]; a.ky = kap->ldim[1]; a.kz = kap->ldim[2];
   a.dx0 = dom.local_min[0]; a.dx1 = dom.local_max[0];
   a.dy0 = dom.local_min[1]; a.dy1 = dom.local_max[1];
   a.dz0 = dom.local_min[2]; a.dz1 = dom.local_max[2];
@@ -458,7 +442,9 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   int box_col[3] = {Geom<double>::HX, kTY, 1};
   if (!EncodeTensorMap3D(&p->map_main, TmaElem::F64, mr.dev, dimv, box_main) ||
       !EncodeTensorMap3D(&p->map_row, TmaElem::F64, mr.dev, dimv, box_row) ||
-      !EncodeTensorMap3D(&p->map_col, TmaElem::F64, mr.dev, dimv, box_col)) {
+      !EncodeTensorMap3D(&p->map_col, TmaElem::F64, mr.dev, dimv, box_col) ||
+      !EncodeTensorMap1D(&p->map_kap, TmaElem::F64, kap->members[0].dev,
+                         (size_t)kap->ldim[0] * kap->ldim[1] * kap->ldim[2], PstagLayout<8>::KBOX)) {
     *why = "grid shape violates a TMA constraint";
     delete p;
     return nullptr;
@@ -471,7 +457,7 @@ void LaunchPstag(Runtime *rt, PstagPlan *p) {
     p->args.sync.wait_epoch = rt->sweep_epoch;
     p->args.sync.signal_epoch = rt->sweep_epoch + 1;
   }
-  void *args[4] = {&p->map_main, &p->map_row, &p->map_col, &p->args};
+  void *args[5] = {&p->map_main, &p->map_row, &p->map_col, &p->map_kap, &p->args};
   PSB_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(p->block), args, p->smem, rt->stream));
 }
 

@@ -94,6 +94,17 @@ __device__ __forceinline__ void load_3d(void *smem_dst, const CUtensorMap *m, ui
       : "memory");
 }
 
+// 1-D tiled load: `box` consecutive elements starting at element c0 of a flat array.  The
+// start coordinate is arbitrary (only the array base must be 16-byte aligned), which is what
+// makes rows of an array whose pitch is not a multiple of 16 bytes loadable by TMA.
+__device__ __forceinline__ void load_1d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0) {
+  asm volatile(
+      "cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0)
+      : "memory");
+}
+
 // Same with an L2 cache-policy operand (createpolicy result).
 __device__ __forceinline__ void load_3d_hint(void *smem_dst, const CUtensorMap *m,
                                              uint64_t *bar, int c0, int c1, int c2,
@@ -127,5 +138,7 @@ enum class TmaElem { F32, F64 };
 // (16-byte strides/alignment, box <= 256 per dim).
 bool EncodeTensorMap3D(CUtensorMap *out, TmaElem elem, const void *base, const int dim[3],
                        const int box[3]);
+// Flat array of `n` elements (n < 2^31) read in boxes of `box` elements.
+bool EncodeTensorMap1D(CUtensorMap *out, TmaElem elem, const void *base, size_t n, int box);
 
 }  // namespace physis_b200
