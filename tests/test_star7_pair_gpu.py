@@ -130,3 +130,46 @@ def test_fused_pair_equal_coefficients(shape, iters, opts, dtype):
     want_b = H.diffusion7_numpy(f0, shape, co, 2 * iters - 1)
     assert np.array_equal(fa.view(view), want_a.view(view))
     assert np.array_equal(fb.view(view), want_b.view(view))
+
+
+def test_full_size_properties_512cubed():
+    """BASELINE config 2's grid (512^3 fp32) at a reduced sweep count, through size-independent
+    properties: the fused schedule equals the sweep-by-sweep schedule bit for bit on both grids
+    (the latter is pinned to the oracle at small sizes), the benchmark's accuracy figure
+    (RMS error against the analytic solution, examples/diffusion-benchmark/baseline.cc:51-60)
+    is at its expected level, and a constant field is a fixed point (cc + 6 c = 1 up to
+    rounding: every point must come out identical)."""
+    from physis_b200 import api
+    n, iters = 512, 12
+    p = H.diffusion_params(n, n, n)
+    co = [float(c) for c in p[:7]]
+    f0 = H.diffusion_initial(n, n, n, p)
+    out = {}
+    for fuse in (0, 1):
+        api.PSInit(dims=(n, n, n))
+        api.set_option(f"star7_fuse={fuse}")
+        a, b = api.Grid((n, n, n), api.PS_FLOAT), api.Grid((n, n, n), api.PS_FLOAT)
+        a.copyin(f0)
+        dom = api.PSDomain3DNew(0, n, 0, n, 0, n)
+        d0 = api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, dom, [a, b], co)
+        d1 = api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, dom, [b, a], co)
+        api.rt().__PSB200ResetStats()
+        api.stencil_run(iters, [d0, d1])
+        assert int(api.stats().fused_pairs) == (10 if fuse else 0)
+        out[fuse] = (a.copyout(), b.copyout())
+        if fuse:
+            const = np.full(n ** 3, 0.3125, np.float32)
+            a.copyin(const)
+            api.stencil_run(iters, [d0, d1])
+            c = a.copyout()
+            assert np.all(c == c[0]) and abs(float(c[0]) - 0.3125) < 1e-5
+        a.free()
+        b.free()
+        api.PSFinalize()
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    assert np.array_equal(out[0][1].view(np.uint32), out[1][1].view(np.uint32))
+    # accuracy against the analytic solution after 2*iters steps
+    t = 2 * iters * float(p[10])
+    exact = H.diffusion_initial(n, n, n, p, time=t)
+    rms = float(np.sqrt(np.mean((out[1][0].astype(np.float64) - exact.astype(np.float64)) ** 2)))
+    assert rms < 1e-5, rms
