@@ -405,7 +405,6 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "star7_sthint") o->star7_sthint = (int)val;
   else if (k == "star7_fuse") o->star7_fuse = (int)val;
   else if (k == "star7_pair_zc") o->star7_pair_zc = (int)val;
-  else if (k == "star7_pair_dbg") o->star7_pair_dbg = (int)val;
   else if (k == "star7_iso") o->star7_iso = (int)val;
   else if (k == "himeno_by") o->himeno_by = (int)val;
   else if (k == "himeno_zc") o->himeno_zc = (int)val;

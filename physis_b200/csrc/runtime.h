@@ -138,7 +138,6 @@ struct Options {
   int star7_fuse = 1;     // 1: a ping-pong pair of whole-grid 7-pt sweeps runs as one fused two-sweep pass
   int star7_pair_zc = 0;  // z chunk of the fused kernel; 0 = automatic
   int star7_iso = 1;      // 1: equal neighbour coefficients use the shared-product form of the fused kernel
-  int star7_pair_dbg = 0; // timing experiments only (results invalid): 1 = no neighbour wait/signal, 2 = no halo stores
   int himeno_by = 0, himeno_zc = 0, himeno_stages = 0, himeno_occ = 0, himeno_carveout = 0;
   int pstag_variant = 4 /* measured best, profiles/r1_tune_pstag_512.csv */, pstag_stages = 0, pstag_occ = 0;
   int time_kernels = 0;        // per-family CUDA-event timing (for bench roofline)

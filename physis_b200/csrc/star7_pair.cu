@@ -600,8 +600,6 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
         const ET *to_hi = (ET *)ml.peer_hi + (size_t)(go->halo - 2) * plane;
         a->push_lo_delta = (const char *)to_lo - (const char *)(a->out + (size_t)a->push_lo_z * plane);
         a->push_hi_delta = (const char *)to_hi - (const char *)(a->out + (size_t)a->push_hi_z * plane);
-        if (o.star7_pair_dbg & 1) a->sync = sweep::SlabSync{};
-        if (o.star7_pair_dbg & 2) a->push_lo_z = a->push_hi_z = -(1 << 30);
       }
       // scalars arrive in the kernel's parameter order: ce, cw, cn, cs, ct, cb, cc
       a->ce = (ET)d0.scalars[0]; a->cw = (ET)d0.scalars[1]; a->cn = (ET)d0.scalars[2];

@@ -20,8 +20,7 @@ lib.run_sweeps_only_physis.argtypes = [C.c_int] * 4 + [C.c_float] * 7
 co = [0.1] * 6 + [0.4]
 n = 512
 count = 400
-configs = [("star7_fuse=0",), ("star7_fuse=1",), ("star7_fuse=1", "star7_pair_dbg=1"),
-           ("star7_fuse=1", "star7_pair_dbg=2"), ("star7_fuse=1", "star7_pair_dbg=3")]
+configs = [("star7_fuse=0",), ("star7_fuse=1",), ("star7_fuse=1", "star7_iso=0")]
 for cfg in configs:
     lib.initialize_physis(0, None, n, n, n * world)
     for kv in cfg:
