@@ -288,6 +288,11 @@ typedef struct {
  * translator/reference_runtime_builder.cc:896-940,1068-1081. */
 float __PSB200StencilRun(int iter, int num_stencils, const __PSB200StencilDesc *descs);
 
+/* How many of the `iter` iterations of a fusable ping-pong pair of sweeps run as fused
+ * two-sweep passes (the rest run sweep by sweep so that both grids end up exactly as the
+ * reference's schedule leaves them, translator/reference_runtime_builder.cc:837-893). */
+int __PSB200FusedPassCount(int iter);
+
 __PSB200Stream __PSB200GetStream(void);
 void __PSB200Synchronize(void);
 

@@ -61,7 +61,7 @@ EXPORTED_SYMBOLS = [
     "__PSGridNew", "__PSGridFree", "__PSGridCopyin", "__PSGridCopyout", "__PSGridSet",
     "__PSGridSwap", "__PSGridGetID", "__PSCheckCudaError", "PSGridCopyin", "PSGridCopyout",
     "PSGridFree", "__PSReduceGridFloat", "__PSReduceGridDouble", "__PSReduceGridInt",
-    "__PSReduceGridLong", "__PSB200StencilRun", "__PSB200GetStream", "__PSB200Synchronize",
+    "__PSReduceGridLong", "__PSB200StencilRun", "__PSB200FusedPassCount", "__PSB200GetStream", "__PSB200Synchronize",
     "__PSB200TimerStart", "__PSB200TimerStopMs", "__PSB200GetStats", "__PSB200ResetStats",
     "__PSB200SetOption", "__PSB200Version", "__PSB200HostAlloc", "__PSB200HostFree", "__ps_trace",
     "__PSB200Rank", "__PSB200WorldSize", "__PSB200GridLocalSize", "__PSB200GridCopyinLocal",

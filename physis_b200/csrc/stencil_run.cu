@@ -219,6 +219,13 @@ const char *SweepName(const SweepPlan *p) { return p->name.c_str(); }
 
 using namespace physis_b200;
 
+// Schedule of a fusable ping-pong pair run for `iter` iterations: the first
+// __PSB200FusedPassCount(iter) iterations run as that many fused two-sweep passes (pass i
+// reads the grid pass i-1 wrote), the rest sweep by sweep.  The count is even, so the newest
+// field is back in the first grid when the single sweeps start, and at least one iteration
+// stays unfused, so the second grid ends up holding the second-newest field.
+extern "C" int __PSB200FusedPassCount(int iter) { return iter >= 3 ? ((iter - 1) & ~1) : 0; }
+
 extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200StencilDesc *descs) {
   Runtime *rt = Runtime::Get();
   // every rank has finished its earlier (synchronous) runtime calls on the grids
@@ -247,11 +254,11 @@ extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200St
   // sweep-by-sweep schedule leaves it.
   int first_unfused = 0;
   Star7PairPlan *pair = nullptr;
-  if (num_stencils == 2 && iter >= 3 && plans[0]->star7 && plans[1]->star7) {
+  if (num_stencils == 2 && __PSB200FusedPassCount(iter) > 0 && plans[0]->star7 && plans[1]->star7) {
     std::string why;
     pair = PrepareStar7Pair(rt, descs[0], descs[1], &why);
     if (pair) {
-      first_unfused = (iter - 1) & ~1;
+      first_unfused = __PSB200FusedPassCount(iter);
       const bool multi = rt->world() > 1;
       if (multi) {
         // single sweeps keep only the halo plane next to the interior current; a fused

@@ -122,3 +122,29 @@ def test_product_sources_do_not_touch_the_oracle():
                     if re.search(r"(import|include|CDLL|dlopen|open)\W.*oracle", text):
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_fused_schedule_leaves_grids_as_the_reference_schedule_does():
+    """Host logic of the fused two-sweep schedule (no GPU): simulate which time level each grid
+    holds.  A fused pass reads one grid and writes level+2 into the other; single sweeps
+    ping-pong.  After `iter` iterations A must hold level 2*iter and B level 2*iter-1."""
+    import ctypes as C
+    import physis_b200
+    lib = physis_b200.load_runtime()
+    lib.__PSB200FusedPassCount.argtypes = [C.c_int]
+    lib.__PSB200FusedPassCount.restype = C.c_int
+    for it in range(0, 200):
+        passes = lib.__PSB200FusedPassCount(it)
+        assert passes % 2 == 0 and 0 <= passes <= max(it - 1, 0)
+        level = {"A": 0, "B": None}
+        src, dst = "A", "B"
+        for _ in range(passes):
+            level[dst] = level[src] + 2
+            src, dst = dst, src
+        assert src == "A"
+        for _ in range(it - passes):
+            level["B"] = level["A"] + 1
+            level["A"] = level["B"] + 1
+        if it > 0:
+            assert level == {"A": 2 * it, "B": 2 * it - 1}, (it, passes, level)
+    assert lib.__PSB200FusedPassCount(500) == 498
