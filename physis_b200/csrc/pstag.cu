@@ -337,6 +337,9 @@ const PstagVariant kPstagVariants[] = {
     PSTAG_VARIANT(8, 1, 1, 2),   // 8: 8 consumer warps of one row each
     PSTAG_VARIANT(4, 1, 1, 4),   // 9
     PSTAG_VARIANT(16, 4, 1, 3),  // 10: 4 consumer warps, 4 rows per thread
+    PSTAG_VARIANT(16, 2, 1, 2),  // 11: 8 consumer warps, two CTAs per SM
+    PSTAG_VARIANT(8, 2, 2, 2),   // 12: 8 consumer warps over two boxes, two CTAs per SM
+    PSTAG_VARIANT(4, 2, 1, 4),   // 13: 2 consumer warps, four CTAs per SM
 };
 constexpr int kNumPstagVariants = sizeof(kPstagVariants) / sizeof(kPstagVariants[0]);
 
