@@ -14,6 +14,9 @@ synthetic input: PSStencilRun of `--count` (default 1000, BASELINE config 2)
           memory + the sweeps + PSGridCopyout, copies inside the timed region
 Timing is on the device (CUDA events on the runtime's stream, through the
 C ABI), max over ranks; the 1 GiB working set is far larger than the 126 MB L2.
+Extra keys on the same line: `himeno` (BASELINE config 3: XL, sweep-only and with
+the per-sweep residual + PSReduce), `periodic_staggered_fp64` (config 5) and
+`strong_scaling_1024` (config 4: a fixed 1024^3 grid cut over the N ranks).
 """
 import argparse
 import ctypes as C
@@ -302,6 +305,47 @@ def himeno_line(args, api, lib, world, dist):
     return out
 
 
+def strong_line(args, api, lib, world, dist):
+    """Extra: BASELINE config 4 -- 7-pt diffusion fp32 on a FIXED 1024^3 grid cut into z-slabs over
+    the ranks (strong scaling; at N=1 the whole grid on one GPU).  Rows of 1024 floats are wider
+    than the fused tile, so this runs sweep by sweep: 8 B/LUP."""
+    n = args.strong_size
+    sweeps = args.strong_count
+    lib.initialize_physis(0, None, n, n, n)
+    lib.initialize_benchmark_physis(n, n, n)
+    zo, zl = C.c_int(), C.c_int()
+    lib.local_size_physis(C.byref(zo), C.byref(zl))
+    i = np.arange(n, dtype=np.float64)
+    ax = (1.0 - np.cos(2 * np.pi * (i + 0.5) / n)).astype(np.float32)
+    az = ax[zo.value:zo.value + zl.value]
+    plane = (0.125 * ax[:, None] * ax[None, :]).astype(np.float32)
+    host, host_ptr = api.pinned_empty(zl.value * n * n * 4, np.float32)
+    hv = host.reshape(zl.value, n, n)
+    for k in range(zl.value):
+        np.multiply(plane, az[k], out=hv[k])
+    lib.copyin_local_physis(host.ctypes.data)
+    co = [0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.4]
+    r = api.rt()
+    lib.run_sweeps_only_physis(20, n, n, n, *co)
+    r.__PSB200Synchronize()
+    _barrier(dist)
+    r.__PSB200ResetStats()
+    r.__PSB200TimerStart()
+    lib.run_sweeps_only_physis(sweeps, n, n, n, *co)
+    ms = r.__PSB200TimerStopMs()
+    _barrier(dist)
+    ms = _max_over_ranks(dist, ms)
+    st = api.stats()
+    lib.finalize_benchmark_physis()
+    r.__PSB200HostFree(C.c_void_p(host_ptr))
+    peak, _ = _peaks()
+    gbs = n ** 3 * sweeps * 8 / ms / 1e6
+    return {"glups": n ** 3 * sweeps / ms / 1e6, "ms_per_sweep": ms / sweeps, "alg_bytes_per_lup": 8,
+            "gbs": gbs, "roofline_frac_per_gpu": gbs / world / peak,
+            "size": f"{n}^3 over {world} GPU(s) ({n}x{n}x{zl.value} z-slab per GPU)", "sweeps": sweeps,
+            "scaling": "strong", "fused_passes": int(st.fused_pairs)}
+
+
 def pstag_line(args, api, lib, world, dist):
     """Extra: BASELINE config 5 -- fp64 periodic 7-pt on a user type {p,q} with a staggered
     coefficient grid, 512^3 cells per GPU (weak scaling), device SoA: 24 B/LUP."""
@@ -474,6 +518,8 @@ def run_b200(args, rank, world, dist):
         ps = pstag_line(args, api, lib, world, dist)
         line["himeno"] = h
         line["periodic_staggered_fp64"] = ps
+    if not args.no_strong and not args.strong and 1024 % world == 0:
+        line["strong_scaling_1024"] = strong_line(args, api, lib, world, dist)
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample()
     if rank == 0:
@@ -496,6 +542,9 @@ def main():
     ap.add_argument("--pstag-size", type=int, default=512)
     ap.add_argument("--pstag-count", type=int, default=100)
     ap.add_argument("--strong", action="store_true", help="keep the global grid at size^3 (strong scaling)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the extra config-4 (1024^3 strong scaling) entry")
+    ap.add_argument("--strong-size", type=int, default=1024)
+    ap.add_argument("--strong-count", type=int, default=100)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     _claim_stdout()

@@ -35,7 +35,7 @@ def test_reference_arm_line():
 @pytest.mark.gpu
 def test_b200_arm_line():
     d = _one_json_line(["--steps", "1", "--warmup", "3", "--size", "128", "--count", "8",
-                        "--no-himeno", "--no-cpu"])
+                        "--no-himeno", "--no-cpu", "--no-strong"])
     for k in COMMON + ["gpu_launches", "roofline", "clocks"]:
         assert k in d, k
     assert "impl" not in d and d["n_gpus"] == 1 and d["dtype"] == "f32" and d["data"] == "synthetic"
