@@ -43,7 +43,9 @@ def case_pair():
     cases = [((128, 32, 16), 3, np.float32, (), co64), ((256, 20, 33), 5, np.float32, ("star7_pair_zc=3",), co64),
              ((512, 17, 24), 4, np.float32, (), iso64), ((64, 30, 19), 6, np.float64, ("star7_pair_zc=2",), co64),
              ((384, 9, 41), 3, np.float32, ("star7_impl=1",), co64), ((128, 21, 26), 5, np.float64, (), iso64),
-             ((256, 12, 35), 4, np.float32, ("star7_pair_zc=6",), iso64)]
+             ((256, 12, 35), 4, np.float32, ("star7_pair_zc=6",), iso64),
+             # slabs of 4+ planes on up to 3 ranks (fused), of 3 planes on 4 ranks (sweep by sweep)
+             ((128, 18, 13), 3, np.float32, (), co64)]
     for shape, iters, dtype, opts, co64 in cases:
         nx, ny, nz = shape
         api.PSInit(["t"], 3, shape)
