@@ -141,7 +141,9 @@ struct Options {
   int himeno_by = 0, himeno_zc = 0, himeno_stages = 0, himeno_occ = 0, himeno_carveout = 0;
   int pstag_variant = 4 /* measured best, profiles/r1_tune_pstag_512.csv */, pstag_stages = 0, pstag_occ = 0;
   int time_kernels = 0;        // per-family CUDA-event timing (for bench roofline)
-  size_t stage_chunk = 32u << 20;  // pinned staging chunk for pageable copies
+  size_t stage_chunk = 64u << 20;  // pinned staging chunk for pageable copies
+  int copy_threads = 0;            // host threads that fill / drain a staging chunk (0 = automatic:
+                                   // up to 8, shared fairly between the ranks of one box)
   // multi-GPU
   int halo = 2;          // halo planes per side of decomposed grids (single sweeps use the one
                          // next to the interior; the fused two-sweep pass needs two)
