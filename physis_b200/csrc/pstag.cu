@@ -69,15 +69,23 @@ struct PstagLayout {
   static constexpr int WEST = SOUTH + Up128(ROWB);
   static constexpr int EAST = WEST + Up128(TY * 16);
   // kap patch: TY+1 rows of TXB+2 vertices (TXB+1 used; the box must be a multiple of 16 bytes)
+  // kap patch: TY+1 rows of TXB+1 vertices in two boxes of the 2-D super-row view (below):
+  // the rows with an even flat row number and those with an odd one, KH rows each
   static constexpr int KAP = EAST + Up128(TY * 16);
   static constexpr int KBOX = Geom<double>::TXB + 4;  // TXB+1 vertices, +1 for an odd start, 16-byte multiple
-  static constexpr int KROW = Up128(KBOX * 8);
-  static constexpr int STRIDE = KAP + (TY + 1) * KROW;
+  static constexpr int KROW = KBOX * 8;               // rows of a box are contiguous in shared memory
+  static constexpr int KH = TY / 2 + 1;
+  static constexpr int KAP_ODD = KAP + Up128(KH * KROW);
+  static constexpr int STRIDE = KAP_ODD + Up128(KH * KROW);
 };
 template <int TY>
 constexpr int PstagBoxStride() { return PstagLayout<TY>::STRIDE; }
 
-template <int TY, int RY, int NBX, int MINB>
+// NS ring stages (3 or 6).  The consumers' loop is unrolled six times -- the least common
+// multiple of the ring depth, the three-plane register window and the two kap planes -- so
+// that every ring slot is an immediate and neither window nor kap registers are ever moved;
+// every work item restarts at slot 0 and the phase parity of each slot is tracked on its own.
+template <int TY, int RY, int NBX, int MINB, int NS>
 __global__ void __launch_bounds__((NBX * (TY / RY) + 1) * 32, MINB)
 PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant__ CUtensorMap map_row,
             const __grid_constant__ CUtensorMap map_col, const __grid_constant__ CUtensorMap map_kap,
@@ -91,6 +99,7 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
   constexpr int BOX_STRIDE = L::STRIDE;
   constexpr int STAGE_BYTES = NBX * BOX_STRIDE;
   constexpr int KROW = L::KROW;
+  static_assert(NS == 3 || NS == 6, "ring depth must divide the unroll factor 6");
 
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -99,10 +108,9 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int S = a.stages;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < NS; ++s) {
       tma::mbar_init(&full[s], 1);
       tma::mbar_init(&empty[s], NW);
     }
@@ -114,13 +122,13 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
   const int tiles_xy = a.ntx * a.nty;
 
   if (warp == NW) {
+    // ------------------------------------------------------------ producer
     if (lane != 0) return;
     tma::prefetch_tensormap(&map_main);
     tma::prefetch_tensormap(&map_row);
     tma::prefetch_tensormap(&map_col);
     tma::prefetch_tensormap(&map_kap);
-    int stage = 0;
-    uint32_t phase = 0;
+    uint32_t epar = 0;  // bit s: parity of the next "slot s is free" phase to wait for
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       const int zci = item / tiles_xy;
       const int txy = item - zci * tiles_xy;
@@ -137,15 +145,23 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
       for (int b = 0; b < NBX; ++b) {
         const int bx0 = x0 + b * G::TXB;
         if (bx0 >= a.nx) continue;
-        tx_bytes += (uint32_t)((TY + 2) * ROWB) + (uint32_t)((TY + 1) * L::KBOX * 8);
+        tx_bytes += (uint32_t)((TY + 2) * ROWB) + (uint32_t)(2 * L::KH * L::KROW);
         if (bx0 == 0) tx_bytes += TY * 16;
         if (bx0 + G::TXB >= a.nx) tx_bytes += TY * 16;
       }
+      int stage = 0;  // every item starts at slot 0
       for (int zz = zb - 1; zz <= ze; ++zz) {
         const int z = a.zwrap ? (zz + a.nz) % a.nz : zz;
-        tma::mbar_wait(&empty[stage], phase ^ 1u);
+        tma::mbar_wait(&empty[stage], ((epar >> stage) & 1u) ^ 1u);
+        epar ^= 1u << stage;
         tma::mbar_arrive_expect_tx(&full[stage], tx_bytes);
         unsigned char *dst = planes + stage * STAGE_BYTES;
+        // kap rows of plane zz (kap does not wrap: it has one more plane than u) as super-rows
+        // of the 2-D view: rows with an even / odd flat row number are the first / second halves
+        const int zk = min(max(zz, 0), a.kz - 1);
+        const int r0 = zk * a.ky + y0;          // flat row number of the patch's first row
+        const int re = (r0 + 1) >> 1;           // super-row of the first even row (r0 or r0+1)
+        const int ro = r0 >> 1;                 // super-row of the first odd row (r0 or r0+1)
 #pragma unroll
         for (int b = 0; b < NBX; ++b) {
           const int bx0 = x0 + b * G::TXB;
@@ -158,35 +174,108 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
             tma::load_3d(bd + L::WEST, &map_col, &full[stage], a.nx - G::HX, y0, z);
           if (bx0 + G::TXB >= a.nx)
             tma::load_3d(bd + L::EAST, &map_col, &full[stage], 0, y0, z);
-          // vertex patch of plane zz (kap does not wrap: it has one more plane than u)
-          const int zk = min(max(zz, 0), a.kz - 1);
-          const int k0 = (zk * a.ky + y0) * a.kx + bx0;
-#pragma unroll
-          for (int rr = 0; rr <= TY; ++rr)
-            tma::load_1d(bd + L::KAP + rr * KROW, &map_kap, &full[stage], (k0 + rr * a.kx) & ~1);
+          // even rows start at column bx0, odd rows at column kx + bx0 of their super-row,
+          // fetched from the even column at or before it (16-byte aligned)
+          tma::load_2d(bd + L::KAP, &map_kap, &full[stage], bx0, re);
+          tma::load_2d(bd + L::KAP_ODD, &map_kap, &full[stage], (a.kx + bx0) & ~1, ro);
         }
-        if (++stage == S) { stage = 0; phase ^= 1u; }
+        if (++stage == NS) stage = 0;
       }
     }
     return;
   }
 
+  // -------------------------------------------------------------- consumers
   const int bx = warp % NBX;
   const int wy = warp / NBX;
-  const int col_off = (G::HX + lane * VEC) * (int)sizeof(double);
   const int row0 = wy * RY;  // first own row inside the MAIN region
-  const int north_off = (wy == 0) ? L::NORTH : (row0 - 1) * ROWB;
-  const int south_off = (wy == NWY - 1) ? L::SOUTH : (row0 + RY) * ROWB;
+  // this thread's first own vector inside a stage, and the rows above / below its rows
+  const unsigned char *my = planes + bx * BOX_STRIDE + row0 * ROWB + (G::HX + lane * VEC) * (int)sizeof(double);
+  const int north_off = (wy == 0) ? L::NORTH - row0 * ROWB : -ROWB;
+  const int south_off = (wy == NWY - 1) ? L::SOUTH - row0 * ROWB : RY * ROWB;
+  const unsigned char *my_kap = planes + bx * BOX_STRIDE + L::KAP + lane * 16;
+  const bool lane_first = (lane == 0), lane_last = (lane == 31);
+  uint32_t fpar = 0;  // bit s: parity of the next "slot s is full" phase to wait for
 
-  int stage = 0;
-  uint32_t phase = 0;
-  auto advance = [&]() {
-    if (++stage == S) { stage = 0; phase ^= 1u; }
-  };
-  auto release = [&](int st) {
-    __syncwarp();
-    if (lane == 0) tma::mbar_arrive(&empty[st]);
-  };
+#define PS_WAIT(SLOT) do { \
+    tma::mbar_wait(&full[(SLOT)], (fpar >> (SLOT)) & 1u); \
+    fpar ^= 1u << (SLOT); \
+  } while (0)
+#define PS_RELEASE(SLOT) do { __syncwarp(); if (lane_first) tma::mbar_arrive(&empty[(SLOT)]); } while (0)
+#define PS_LOAD(DST, SLOT) do { \
+    const unsigned char *p__ = my + (SLOT) * STAGE_BYTES; \
+    _Pragma("unroll") for (int r = 0; r < RY; ++r) DST[r] = *reinterpret_cast<const double2 *>(p__ + r * ROWB); \
+  } while (0)
+  // this thread's 3 x (RY+1) vertices of kap plane KZ, which arrived in ring slot SLOT: patch
+  // row q has flat row number R = KZ*ky + ytile + q; the rows with even R are in the first
+  // box, those with odd R in the second (whose first wanted column is `kodd` elements in),
+  // and in either box row q is row q/2
+#define PS_LOAD_KAP(K, SLOT, KZ) do { \
+    const unsigned char *kp__ = my_kap + (SLOT) * STAGE_BYTES; \
+    const int p0__ = ((KZ) * a.ky + ytile) & 1; \
+    _Pragma("unroll") for (int r = 0; r <= RY; ++r) { \
+      const int q__ = row0 + r; \
+      const int odd__ = (p0__ + q__) & 1; \
+      const double *src__ = reinterpret_cast<const double *>( \
+          kp__ + odd__ * (L::KAP_ODD - L::KAP) + (q__ >> 1) * KROW) + odd__ * kodd; \
+      K[r][0] = src__[0]; K[r][1] = src__[1]; K[r][2] = src__[2]; \
+    } \
+  } while (0)
+  // One plane z: the centre plane is in registers (CEN) and in slot CS, the top plane arrives
+  // in slot TS together with kap plane z+1.
+#define PS_STEP(CS, TS, BOT, CEN, TOP, KLO, KHI) do { \
+    PS_WAIT(TS); \
+    PS_LOAD(TOP, TS); \
+    PS_LOAD_KAP(KHI, TS, z + 1); \
+    const unsigned char *cb = my + (CS) * STAGE_BYTES; \
+    const double2 north = *reinterpret_cast<const double2 *>(cb + north_off); \
+    const double2 south = *reinterpret_cast<const double2 *>(cb + south_off); \
+    _Pragma("unroll") for (int r = 0; r < RY; ++r) { \
+      const double2 c = CEN[r]; \
+      double wv = __shfl_up_sync(0xffffffffu, c.y, 1); \
+      double ev = __shfl_down_sync(0xffffffffu, c.x, 1); \
+      if (lane_first) wv = *reinterpret_cast<const double *>(cb + w_off + r * w_str); \
+      if (need_e) ev = *reinterpret_cast<const double *>(cb + e_off + r * e_str); \
+      const double2 nv = (r == 0) ? north : CEN[r > 0 ? r - 1 : 0]; \
+      const double2 sv = (r == RY - 1) ? south : CEN[r < RY - 1 ? r + 1 : r]; \
+      const double2 bv = BOT[r], tv = TOP[r]; \
+      double2 o; \
+      _Pragma("unroll") for (int j = 0; j < VEC; ++j) { \
+        const double cj = Elem(c, j); \
+        const double wj = (j == 0) ? wv : c.x; \
+        const double ej = (j == VEC - 1) ? ev : c.y; \
+        /* 0.125 * (k000 + k100 + k010 + k001 + k110 + k101 + k011 + k111) */ \
+        double ks = AddRn(KLO[r][j], KLO[r][j + 1]); \
+        ks = AddRn(ks, KLO[r + 1][j]); \
+        ks = AddRn(ks, KHI[r][j]); \
+        ks = AddRn(ks, KLO[r + 1][j + 1]); \
+        ks = AddRn(ks, KHI[r][j + 1]); \
+        ks = AddRn(ks, KHI[r + 1][j]); \
+        ks = AddRn(ks, KHI[r + 1][j + 1]); \
+        const double k = MulRn(0.125, ks); \
+        /* w + e + n + s + b + t - 6.0*c */ \
+        double acc = AddRn(wj, ej); \
+        acc = AddRn(acc, Elem(nv, j)); \
+        acc = AddRn(acc, Elem(sv, j)); \
+        acc = AddRn(acc, Elem(bv, j)); \
+        acc = AddRn(acc, Elem(tv, j)); \
+        acc = SubRn(acc, MulRn(6.0, cj)); \
+        SetElem(o, j, AddRn(cj, MulRn(k, acc))); \
+      } \
+      if (st_ok[r]) { \
+        *reinterpret_cast<double2 *>(obase + (size_t)r * a.nx) = o; \
+        if (pushing) { \
+          if (z == a.push_lo_z) *reinterpret_cast<double2 *>(a.push_lo + prow + (size_t)r * a.nx) = o; \
+          if (z == a.push_hi_z) *reinterpret_cast<double2 *>(a.push_hi + prow + (size_t)r * a.nx) = o; \
+        } \
+      } \
+    } \
+    obase += plane_elems; \
+    PS_RELEASE(CS); \
+  } while (0)
+
+  const size_t plane_elems = (size_t)a.nx * a.ny;
+  const bool pushing = (a.push_lo_z >= 0) || (a.push_hi_z >= 0);
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
     const int zci = item / tiles_xy;
@@ -198,133 +287,86 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
     const int ybase = a.dy0 + ty * TY + wy * RY;
     const int zb = a.dz0 + zci * a.zc;
     const int ze = min(zb + a.zc, a.dz1);
-    const bool x_ok = (x >= a.dx0) && (x + VEC <= a.dx1);
-    const bool x_first = (x == 0);
-    const bool x_last = (x + VEC == a.nx);
-    const bool in_grid = x < a.nx;
+    const bool x_ok = (x >= a.dx0) && (x + VEC <= a.dx1) && (x < a.nx);
+    // x neighbours of lane 0 / lane 31: the box's own x halo, or on the periodic faces the
+    // wrap column (16 bytes per row: x = nx-2, nx-1 west of the grid, x = 0, 1 east of it)
+    const int own = row0 * ROWB + (G::HX + lane * VEC) * (int)sizeof(double);  // of `my` inside a box
+    const bool x_first = (x == 0), x_last = (x + VEC == a.nx);
+    const int w_off = x_first ? L::WEST + row0 * 16 + 8 - own : -(int)sizeof(double);
+    const int w_str = x_first ? 16 : ROWB;
+    const int e_off = x_last ? L::EAST + row0 * 16 - own : VEC * (int)sizeof(double);
+    const int e_str = x_last ? 16 : ROWB;
+    const bool need_e = lane_last || x_last;  // (the last column need not sit in lane 31)
+    bool st_ok[RY];
+#pragma unroll
+    for (int r = 0; r < RY; ++r) st_ok[r] = x_ok && (ybase + r) >= a.dy0 && (ybase + r) < a.dy1;
+    const size_t prow = (size_t)ybase * a.nx + x;
+    double *obase = a.out + (size_t)zb * plane_elems + prow;
+    const int ytile = a.dy0 + ty * TY;  // first row of the tile (= of the kap patch)
+    const int kodd = (a.kx + bx0) & 1;  // the odd rows' box starts at the even column at or before theirs
 
-    const unsigned char *box = planes + bx * BOX_STRIDE;
-    double2 cen[RY], bot[RY], top[RY];
-    // kap values at plane z (lo) and z+1 (hi): rows ybase .. ybase+RY, x .. x+2
-    double klo[RY + 1][3], khi[RY + 1][3];
+    double2 w0[RY], w1[RY], w2[RY];            // z window of own cells; roles rotate
+    double ka[RY + 1][3], kb[RY + 1][3];       // kap planes z and z+1; roles alternate
 
-    // this thread's 3 x (RY+1) vertices of the kap plane that arrived in ring stage `st`
-    // (kz = the kap plane: row r of the patch starts at flat element e, fetched from e & ~1)
-    auto load_kap = [&](double (&k)[RY + 1][3], int st, int kz) {
-      const unsigned char *kp = box + st * STAGE_BYTES + L::KAP + row0 * KROW + lane * 16;
-      const int e0 = (kz * a.ky + (ybase - wy * RY) + row0) * a.kx + bx0;
-#pragma unroll
-      for (int r = 0; r <= RY; ++r) {
-        const double *src = reinterpret_cast<const double *>(kp + r * KROW) + ((e0 + r * a.kx) & 1);
-        k[r][0] = src[0]; k[r][1] = src[1]; k[r][2] = src[2];
-      }
-    };
+    // plane zb-1 -> bottom (slot 0), plane zb -> centre (slot 1, with kap plane zb)
+    PS_WAIT(0);
+    PS_LOAD(w0, 0);
+    PS_RELEASE(0);
+    PS_WAIT(1);
+    PS_LOAD(w1, 1);
+    PS_LOAD_KAP(ka, 1, zb);
 
-    // plane zb-1 -> bot
-    tma::mbar_wait(&full[stage], phase);
-    {
-      const unsigned char *p = box + stage * STAGE_BYTES + row0 * ROWB + col_off;
-#pragma unroll
-      for (int r = 0; r < RY; ++r) bot[r] = *reinterpret_cast<const double2 *>(p + r * ROWB);
-    }
-    release(stage);
-    advance();
-    int stage_c = stage;
-    tma::mbar_wait(&full[stage], phase);
-    {
-      const unsigned char *p = box + stage * STAGE_BYTES + row0 * ROWB + col_off;
-#pragma unroll
-      for (int r = 0; r < RY; ++r) cen[r] = *reinterpret_cast<const double2 *>(p + r * ROWB);
-    }
-    load_kap(klo, stage_c, zb);   // kap(zb) came with plane zb
-    advance();
-
-    for (int z = zb; z < ze; ++z) {
-      const int stage_t = stage;
-      tma::mbar_wait(&full[stage], phase);
-      load_kap(khi, stage_t, z + 1);   // kap(z+1) came with plane z+1
-      {
-        const unsigned char *p = box + stage * STAGE_BYTES + row0 * ROWB + col_off;
-#pragma unroll
-        for (int r = 0; r < RY; ++r) top[r] = *reinterpret_cast<const double2 *>(p + r * ROWB);
+    int z = zb;
+    if (NS == 6) {
+      for (;;) {
+        PS_STEP(1, 2, w0, w1, w2, ka, kb);
+        if (++z >= ze) { PS_RELEASE(2); break; }
+        PS_STEP(2, 3, w1, w2, w0, kb, ka);
+        if (++z >= ze) { PS_RELEASE(3); break; }
+        PS_STEP(3, 4, w2, w0, w1, ka, kb);
+        if (++z >= ze) { PS_RELEASE(4); break; }
+        PS_STEP(4, 5, w0, w1, w2, kb, ka);
+        if (++z >= ze) { PS_RELEASE(5); break; }
+        PS_STEP(5, 0, w1, w2, w0, ka, kb);
+        if (++z >= ze) { PS_RELEASE(0); break; }
+        PS_STEP(0, 1, w2, w0, w1, kb, ka);
+        if (++z >= ze) { PS_RELEASE(1); break; }
       }
-      const unsigned char *cb = box + stage_c * STAGE_BYTES;
-      double *const push0 = (z == a.push_lo_z) ? a.push_lo : nullptr;
-      double *const push1 = (z == a.push_hi_z) ? a.push_hi : nullptr;
-      const double2 north = *reinterpret_cast<const double2 *>(cb + north_off + col_off);
-      const double2 south = *reinterpret_cast<const double2 *>(cb + south_off + col_off);
-#pragma unroll
-      for (int r = 0; r < RY; ++r) {
-        const int y = ybase + r;
-        const double2 c = cen[r];
-        double wv = __shfl_up_sync(0xffffffffu, c.y, 1);
-        double ev = __shfl_down_sync(0xffffffffu, c.x, 1);
-        const unsigned char *rowp = cb + (row0 + r) * ROWB;
-        if (lane == 0) wv = *reinterpret_cast<const double *>(rowp + (G::HX - 1) * sizeof(double));
-        if (lane == 31) ev = *reinterpret_cast<const double *>(rowp + (G::HX + G::TXB) * sizeof(double));
-        // periodic wrap in x: the wrap columns hold x = nx-2,nx-1 (west) and x = 0,1 (east)
-        if (x_first) wv = *reinterpret_cast<const double *>(cb + L::WEST + (row0 + r) * 16 + 8);
-        if (x_last) ev = *reinterpret_cast<const double *>(cb + L::EAST + (row0 + r) * 16);
-        const double2 nv = (r == 0) ? north : cen[r - 1];
-        const double2 sv = (r == RY - 1) ? south : cen[r + 1];
-        const double2 bv = bot[r], tv = top[r];
-        double2 o;
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          const double cj = Elem(c, j);
-          const double wj = (j == 0) ? wv : c.x;
-          const double ej = (j == VEC - 1) ? ev : c.y;
-          // 0.125 * (k000 + k100 + k010 + k001 + k110 + k101 + k011 + k111)
-          double ks = AddRn(klo[r][j], klo[r][j + 1]);
-          ks = AddRn(ks, klo[r + 1][j]);
-          ks = AddRn(ks, khi[r][j]);
-          ks = AddRn(ks, klo[r + 1][j + 1]);
-          ks = AddRn(ks, khi[r][j + 1]);
-          ks = AddRn(ks, khi[r + 1][j]);
-          ks = AddRn(ks, khi[r + 1][j + 1]);
-          const double k = MulRn(0.125, ks);
-          // w + e + n + s + b + t - 6.0*c
-          double acc = AddRn(wj, ej);
-          acc = AddRn(acc, Elem(nv, j));
-          acc = AddRn(acc, Elem(sv, j));
-          acc = AddRn(acc, Elem(bv, j));
-          acc = AddRn(acc, Elem(tv, j));
-          acc = SubRn(acc, MulRn(6.0, cj));
-          SetElem(o, j, AddRn(cj, MulRn(k, acc)));
-        }
-        if (x_ok && in_grid && y >= a.dy0 && y < a.dy1) {
-          double2 *dst = reinterpret_cast<double2 *>(a.out + ((size_t)z * a.ny + y) * a.nx + x);
-          *dst = o;
-          if (push0) *reinterpret_cast<double2 *>(push0 + (size_t)y * a.nx + x) = o;
-          if (push1) *reinterpret_cast<double2 *>(push1 + (size_t)y * a.nx + x) = o;
-        }
-      }
-      release(stage_c);
-      stage_c = stage_t;
-      advance();
-#pragma unroll
-      for (int r = 0; r < RY; ++r) {
-        bot[r] = cen[r];
-        cen[r] = top[r];
-      }
-#pragma unroll
-      for (int r = 0; r <= RY; ++r) {
-        klo[r][0] = khi[r][0]; klo[r][1] = khi[r][1]; klo[r][2] = khi[r][2];
+    } else {
+      for (;;) {
+        PS_STEP(1, 2, w0, w1, w2, ka, kb);
+        if (++z >= ze) { PS_RELEASE(2); break; }
+        PS_STEP(2, 0, w1, w2, w0, kb, ka);
+        if (++z >= ze) { PS_RELEASE(0); break; }
+        PS_STEP(0, 1, w2, w0, w1, ka, kb);
+        if (++z >= ze) { PS_RELEASE(1); break; }
+        PS_STEP(1, 2, w0, w1, w2, kb, ka);
+        if (++z >= ze) { PS_RELEASE(2); break; }
+        PS_STEP(2, 0, w1, w2, w0, ka, kb);
+        if (++z >= ze) { PS_RELEASE(0); break; }
+        PS_STEP(0, 1, w2, w0, w1, kb, ka);
+        if (++z >= ze) { PS_RELEASE(1); break; }
       }
     }
-    release(stage_c);
   }
   SlabSyncSignal(a.sync, NW * 32, threadIdx.x == 0);
+#undef PS_STEP
+#undef PS_LOAD_KAP
+#undef PS_LOAD
+#undef PS_RELEASE
+#undef PS_WAIT
 }
 
 // tile shapes (rows, rows per thread, boxes side by side); selected by option pstag_variant
 struct PstagVariant {
   int ty, ry, nbx;
-  const void *fn;
+  int ctas_per_sm;        // the occupancy the shape is meant for (more resident CTAs measured slower)
+  const void *fn6, *fn3;  // ring of 6 / 3 stages
   size_t box_stride;
 };
 #define PSTAG_VARIANT(TY, RY, NBX, MINB) \
-  { TY, RY, NBX, (const void *)PstagKernel<TY, RY, NBX, MINB>, (size_t)PstagBoxStride<TY>() }
+  { TY, RY, NBX, MINB, (const void *)PstagKernel<TY, RY, NBX, MINB, 6>, \
+    (const void *)PstagKernel<TY, RY, NBX, MINB, 3>, (size_t)PstagBoxStride<TY>() }
 const PstagVariant kPstagVariants[] = {
     PSTAG_VARIANT(16, 2, 2, 1),  // 0: 16 consumer warps (register-capped at 96: spills)
     PSTAG_VARIANT(8, 2, 2, 1),   // 1: 8 consumer warps
@@ -356,6 +398,20 @@ struct PstagPlan {
   int wr_member = 0;
 };
 
+// kap's rows have a pitch of (N+1)*8 bytes, not a 16-byte multiple, so kap cannot be a 3-D TMA
+// tensor.  Two consecutive rows together are ((N+1)*16 bytes), so the flat array is described
+// as a 2-D tensor of "super-rows" of two rows each: one box fetches the rows of a tile's
+// vertex patch with an even flat row number (first halves of their super-rows), a second box
+// those with an odd one (second halves).  The last super-row may extend one row past the
+// array; grid allocations carry slack for that (runtime.cu, kAllocSlack).
+static bool EncodeKapMap(CUtensorMap *out, const Grid *kap, int ty) {
+  const size_t kx = kap->ldim[0];
+  const size_t rows = (size_t)kap->ldim[1] * kap->ldim[2];
+  const int dim[2] = {(int)(2 * kx), (int)((rows + 1) / 2)};
+  const int box[2] = {PstagLayout<8>::KBOX, ty / 2 + 1};
+  return EncodeTensorMap2D(out, TmaElem::F64, kap->members[0].dev, dim, box);
+}
+
 PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *why) {
   if (d.num_grids != 2) { *why = "expects grids {u, kap}"; return nullptr; }
   Grid *u = Grid::FromHandle(d.grids[0]);
@@ -378,9 +434,9 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
     *why = "x extent and domain x-range must be even"; return nullptr;
   }
   int vi = rt->opt.pstag_variant;
-  if (vi < 0 || vi >= kNumPstagVariants) vi = 4;
-  // the default tile is 8 rows; grids whose y extent is not a multiple of it try 4 rows
-  if (ny % kPstagVariants[vi].ty != 0 && ny % 4 == 0) vi = 9;
+  if (vi < 0 || vi >= kNumPstagVariants) vi = 13;
+  // grids whose y extent is not a multiple of the chosen tile height try 4 rows
+  if (ny % kPstagVariants[vi].ty != 0 && ny % 4 == 0) vi = 13;
   const PstagVariant &V = kPstagVariants[vi];
   const int kTY = V.ty, kRY = V.ry, kNBX = V.nbx;
   if (ny % kTY != 0 || (dom.local_min[1] % kTY) != 0) { *why = "y extent must be a multiple of the tile height"; return nullptr; }
@@ -392,18 +448,17 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   if (dom.local_min[0] != 0) { *why = "domain must start at x = 0"; return nullptr; }
 
   PstagPlan *p = new PstagPlan();
-  p->fn = V.fn;
-  int stages = rt->opt.pstag_stages > 0 ? std::min(rt->opt.pstag_stages, kMaxStages) : 6;
-  if (stages < 3) stages = 3;
-  while (stages > 3 && kBarrierBytes + (size_t)stages * kNBX * V.box_stride > 227 * 1024)
-    --stages;
+  // ring depth 6, or 3 where six stages do not fit the SM (or option pstag_stages <= 3)
+  int stages = (rt->opt.pstag_stages > 0 && rt->opt.pstag_stages <= 3) ? 3 : 6;
+  if (kBarrierBytes + (size_t)stages * kNBX * V.box_stride > 227 * 1024) stages = 3;
+  p->fn = stages == 6 ? V.fn6 : V.fn3;
   p->smem = kBarrierBytes + (size_t)stages * kNBX * V.box_stride;
   p->block = (kNBX * (kTY / kRY) + 1) * 32;
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   int occ = 0;
   PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->fn, p->block, p->smem));
   PSB_CHECK(occ > 0, "pstag kernel does not fit on an SM");
-  if (rt->opt.pstag_occ > 0) occ = std::min(occ, rt->opt.pstag_occ);
+  occ = std::min(occ, rt->opt.pstag_occ > 0 ? rt->opt.pstag_occ : V.ctas_per_sm);
 
   PstagArgs &a = p->args;
   p->wr_member = wr;
@@ -446,8 +501,7 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   if (!EncodeTensorMap3D(&p->map_main, TmaElem::F64, mr.dev, dimv, box_main) ||
       !EncodeTensorMap3D(&p->map_row, TmaElem::F64, mr.dev, dimv, box_row) ||
       !EncodeTensorMap3D(&p->map_col, TmaElem::F64, mr.dev, dimv, box_col) ||
-      !EncodeTensorMap1D(&p->map_kap, TmaElem::F64, kap->members[0].dev,
-                         (size_t)kap->ldim[0] * kap->ldim[1] * kap->ldim[2], PstagLayout<8>::KBOX)) {
+      !EncodeKapMap(&p->map_kap, kap, kTY)) {
     *why = "grid shape violates a TMA constraint";
     delete p;
     return nullptr;

@@ -10,6 +10,7 @@
 //   PSDomainNDNew runtime/libphysis_rt_cuda.cc:142-160
 // Error handling: print + exit (runtime_common_cuda.h:16-27).
 #include "runtime.h"
+#include "tma.cuh"
 
 #include <thread>
 
@@ -25,19 +26,23 @@ namespace physis_b200 {
 
 // ---------------------------------------------------------------- buffers
 
+static constexpr size_t kAllocSlack = 128u << 10;
+
 bool DeviceBuffer::Allocate(size_t bytes, cudaStream_t stream) {
   PSB_CHECK(ptr_ == nullptr, "DeviceBuffer::Allocate on a live buffer");
   if (bytes == 0) {
     size_ = capacity_ = 0;
     return true;
   }
-  cudaError_t e = cudaMalloc(&ptr_, bytes);
+  // kAllocSlack: TMA views that regroup an array (pstag.cu: two rows per "super-row") may
+  // describe up to one row past its end; the slack keeps such reads inside the allocation
+  cudaError_t e = cudaMalloc(&ptr_, bytes + kAllocSlack);
   if (e != cudaSuccess) {
     cudaGetLastError();  // clear
     ptr_ = nullptr;
     return false;
   }
-  PSB_CUDA(cudaMemsetAsync(ptr_, 0, bytes, stream));
+  PSB_CUDA(cudaMemsetAsync(ptr_, 0, bytes + kAllocSlack, stream));
   size_ = capacity_ = bytes;
   return true;
 }
@@ -450,6 +455,7 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "copyout_gather") o->copyout_gather = (int)val;
   else if (k == "stage_chunk_mb") o->stage_chunk = (size_t)val << 20;
   else if (k == "copy_threads") o->copy_threads = (int)val;
+  else if (k == "tma_l2promo") g_tma_l2_promotion = (int)val;
   else return -1;
   return 0;
 }

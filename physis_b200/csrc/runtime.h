@@ -139,7 +139,7 @@ struct Options {
   int star7_pair_zc = 0;  // z chunk of the fused kernel; 0 = automatic
   int star7_iso = 1;      // 1: equal neighbour coefficients use the shared-product form of the fused kernel
   int himeno_by = 0, himeno_zc = 0, himeno_stages = 0, himeno_occ = 0, himeno_carveout = 0;
-  int pstag_variant = 4 /* measured best, profiles/r1_tune_pstag_512.csv */, pstag_stages = 0, pstag_occ = 0;
+  int pstag_variant = 13 /* measured best, profiles/r1_tune_pstag_512.csv */, pstag_stages = 0, pstag_occ = 0;
   int time_kernels = 0;        // per-family CUDA-event timing (for bench roofline)
   size_t stage_chunk = 64u << 20;  // pinned staging chunk for pageable copies
   int copy_threads = 0;            // host threads that fill / drain a staging chunk (0 = automatic:

@@ -8,7 +8,17 @@
 
 namespace physis_b200 {
 
+int g_tma_l2_promotion = 3;  // 0 none, 1 64 B, 2 128 B, 3 256 B (option tma_l2promo)
+
 namespace {
+CUtensorMapL2promotion Promo() {
+  switch (g_tma_l2_promotion) {
+    case 0: return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    case 1: return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+    case 2: return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    default: return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }
+}
 using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                               const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                               const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -43,7 +53,27 @@ bool EncodeTensorMap3D(CUtensorMap *out, TmaElem elem, const void *base, const i
   CUresult r = ResolveEncode()(
       out, elem == TmaElem::F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
       3, const_cast<void *>(base), gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_SWIZZLE_NONE, Promo(),
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool EncodeTensorMap2D(CUtensorMap *out, TmaElem elem, const void *base, const int dim[2],
+                       const int box[2]) {
+  const size_t es = elem == TmaElem::F64 ? 8 : 4;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+  if (((size_t)dim[0] * es) % 16 != 0) return false;
+  for (int i = 0; i < 2; ++i)
+    if (box[i] < 1 || box[i] > 256 || dim[i] < 1) return false;
+  if (((size_t)box[0] * es) % 16 != 0) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)dim[0], (cuuint64_t)dim[1]};
+  cuuint64_t gstride[1] = {(cuuint64_t)dim[0] * es};
+  cuuint32_t bdim[2] = {(cuuint32_t)box[0], (cuuint32_t)box[1]};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ResolveEncode()(
+      out, elem == TmaElem::F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+      2, const_cast<void *>(base), gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_NONE, Promo(),
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -59,7 +89,7 @@ bool EncodeTensorMap1D(CUtensorMap *out, TmaElem elem, const void *base, size_t 
   CUresult r = ResolveEncode()(
       out, elem == TmaElem::F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
       1, const_cast<void *>(base), gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_SWIZZLE_NONE, Promo(),
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }

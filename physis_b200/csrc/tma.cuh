@@ -105,6 +105,16 @@ __device__ __forceinline__ void load_1d(void *smem_dst, const CUtensorMap *m, ui
       : "memory");
 }
 
+__device__ __forceinline__ void load_2d(void *smem_dst, const CUtensorMap *m, uint64_t *bar,
+                                        int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // Same with an L2 cache-policy operand (createpolicy result).
 __device__ __forceinline__ void load_3d_hint(void *smem_dst, const CUtensorMap *m,
                                              uint64_t *bar, int c0, int c1, int c2,
@@ -133,11 +143,15 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
 // Host side: cuTensorMapEncodeTiled through the runtime's driver entry point
 // lookup (no link-time dependency on libcuda).
 enum class TmaElem { F32, F64 };
+extern int g_tma_l2_promotion;  // L2 promotion of every tensor map encoded from now on (tuning)
 // Describes a dense 3-D array (x fastest) of `dim` elements and a box of
 // `box` elements; returns false if the shape violates a TMA constraint
 // (16-byte strides/alignment, box <= 256 per dim).
 bool EncodeTensorMap3D(CUtensorMap *out, TmaElem elem, const void *base, const int dim[3],
                        const int box[3]);
+// Dense 2-D array (x fastest) of `dim` elements read in boxes of `box` elements.
+bool EncodeTensorMap2D(CUtensorMap *out, TmaElem elem, const void *base, const int dim[2],
+                       const int box[2]);
 // Flat array of `n` elements (n < 2^31) read in boxes of `box` elements.
 bool EncodeTensorMap1D(CUtensorMap *out, TmaElem elem, const void *base, size_t n, int box);
 

@@ -24,7 +24,7 @@ lib.pstag_copyin_local(u.ctypes.data, kap.ctypes.data)
 lib.pstag_sweeps_only.argtypes = [C.c_int] * 4
 r = api.rt()
 rows = []
-for v, st, occ in itertools.product([4, 6, 11, 12, 13], [4, 5, 6, 7, 8], [0]):
+for v, st, occ in itertools.product([4, 13, 8, 1, 6, 11], [3, 6], [0, 1, 2, 3, 4]):
     api.set_option(f"pstag_variant={v}")
     api.set_option(f"pstag_stages={st}")
     api.set_option(f"pstag_occ={occ}")
