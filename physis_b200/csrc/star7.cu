@@ -646,16 +646,18 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   const int slots = rt->sm_count * occ;
   int zc = o.star7_zc;
   if (zc <= 0) {
-    // fewest z chunks (least z-halo re-reads) that still give every resident
-    // CTA slot at least ~2 items, chunk count chosen so items divide the slots
-    // as evenly as possible
-    // short chunks keep the statically strided items balanced across CTAs (the
-    // two extra halo planes per chunk mostly hit in L2); 32 planes measured best
-    // at 512^3, shrink further only when there would be fewer than ~4 items per slot
-    int tiles = ntx * nty;
-    int want_chunks = std::max(1, CeilDiv(4L * slots, tiles));
-    zc = std::min(32, std::max(8, CeilDiv(nzd, want_chunks)));
-    zc = std::min(zc, nzd);
+    // every z chunk re-reads two planes, and the statically strided items run in waves of
+    // `slots`: take the chunk count with the least total plane work per CTA slot (measured:
+    // 32 planes at 512^3 with 64 full-row tiles, 128 planes at 1024x1024x512 with 256 tiles)
+    const int tiles = ntx * nty;
+    long best_cost = -1;
+    for (int n = 1; n <= std::max(1, nzd / 8); ++n) {
+      const int c = CeilDiv(nzd, n);
+      const long waves = CeilDiv((long)tiles * CeilDiv(nzd, c), slots);
+      const long cost = waves * (c + 2);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; zc = c; }
+    }
+    if (zc <= 0) zc = nzd;
   }
   const int nzc = CeilDiv(nzd, zc);
   const int nitems = ntx * nty * nzc;
