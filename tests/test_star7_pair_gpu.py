@@ -173,3 +173,38 @@ def test_full_size_properties_512cubed():
     exact = H.diffusion_initial(n, n, n, p, time=t)
     rms = float(np.sqrt(np.mean((out[1][0].astype(np.float64) - exact.astype(np.float64)) ** 2)))
     assert rms < 1e-5, rms
+
+
+def test_config2_full_run_fused_equals_sweep_by_sweep():
+    """BASELINE config 2 in full -- 512^3 fp32, 1000 sweeps, the benchmark's own coefficients
+    (equal neighbour coefficients: the shared-product form) -- the fused schedule (498 two-sweep
+    passes + 4 single sweeps) against the sweep-by-sweep schedule: both grids bit-identical."""
+    from physis_b200 import api
+    n, iters = 512, 500
+    p = H.diffusion_params(n, n, n)
+    co = [float(c) for c in p[:7]]
+    f0 = H.diffusion_initial(n, n, n, p)
+    out = {}
+    for fuse in (0, 1):
+        api.PSInit(dims=(n, n, n))
+        api.set_option(f"star7_fuse={fuse}")
+        a, b = api.Grid((n, n, n), api.PS_FLOAT), api.Grid((n, n, n), api.PS_FLOAT)
+        a.copyin(f0)
+        dom = api.PSDomain3DNew(0, n, 0, n, 0, n)
+        d0 = api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, dom, [a, b], co)
+        d1 = api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, dom, [b, a], co)
+        api.rt().__PSB200ResetStats()
+        api.stencil_run(iters, [d0, d1])
+        st = api.stats()
+        assert int(st.fused_pairs) == (498 if fuse else 0)
+        assert int(st.kernel_launches) == (502 if fuse else 1000)
+        out[fuse] = (a.copyout(), b.copyout())
+        a.free()
+        b.free()
+        api.PSFinalize()
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    assert np.array_equal(out[0][1].view(np.uint32), out[1][1].view(np.uint32))
+    # the field is still the smooth decaying mode: compare with the analytic solution
+    exact = H.diffusion_initial(n, n, n, p, time=2 * iters * float(p[10]))
+    rms = float(np.sqrt(np.mean((out[1][0].astype(np.float64) - exact.astype(np.float64)) ** 2)))
+    assert rms < 1e-4, rms
