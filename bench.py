@@ -122,6 +122,31 @@ def _emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+_ORIG_AFFINITY = None
+
+
+def _bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs next to its GPU (NVML's affinity mask), so that its pinned host
+    buffers are allocated in that socket's memory: with 8 ranks copying at once the host side of
+    the PCIe transfers is the bottleneck of `e2e`.  Best effort; returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < ncpu:
+            global _ORIG_AFFINITY
+            _ORIG_AFFINITY = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} of {ncpu} CPUs (GPU {local_rank}'s NUMA node)"
+        return "no narrower affinity reported"
+    except Exception as e:  # noqa: BLE001 -- NVML absent or not permitted: run unbound
+        return f"unbound ({type(e).__name__})"
+
+
 def _dist_setup(ngpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -248,6 +273,8 @@ def cpu_baseline_sample():
     """Config 1 (256^3, 100 sweeps) on the host cores: the reference's OpenMP form on all
     threads and the Physis REFERENCE target on one (its codegen is sequential)."""
     import helpers as H
+    if _ORIG_AFFINITY is not None:   # the CPU baseline gets every host core back
+        os.sched_setaffinity(0, _ORIG_AFFINITY)
     n, sweeps = 256, 100
     lib = H.oracle_ref()
     if lib is None:
@@ -503,7 +530,7 @@ def run_b200(args, rank, world, dist):
                    "parallelism": f"z-slabs x{world}, halo planes stored peer-to-peer by the sweep",
                    "schedule": (f"{pairs // max(args.steps, 1)} fused two-sweep passes + "
                                 f"{(launches - pairs) // max(args.steps, 1)} single sweeps per step"),
-                   "options": args.opt},
+                   "options": args.opt, "cpu_binding": args.cpu_binding},
         "e2e": {"value": e2e, "unit": "GLUP/s", "h2d_bytes_per_step": npts_loc * 4 * world,
                 "d2h_bytes_per_step": npts_loc * 4 * world, "ms_per_step": ms_e2e / args.steps,
                 "checksum": checksum},
@@ -553,6 +580,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    args.cpu_binding = _bind_to_gpu_numa_node(int(os.environ.get("LOCAL_RANK", "0")))
     rank, world, dist = _dist_setup(args.gpus)
     run_b200(args, rank, world, dist)
     if dist is not None:
