@@ -12,6 +12,7 @@
 #include "runtime.h"
 #include "tma.cuh"
 
+#include <system_error>
 #include <thread>
 
 #include <algorithm>
@@ -352,12 +353,20 @@ static void StageCopy(void *dst, const void *src, size_t n, int threads) {
   const size_t part = ((n + t - 1) / t + 4095) & ~(size_t)4095;
   std::vector<std::thread> pool;
   pool.reserve(t - 1);
+  size_t done_to = std::min(part, n);  // [0, done_to) is this thread's share
   for (int i = 1; i < t; ++i) {
     const size_t off = (size_t)i * part;
     if (off >= n) break;
-    pool.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, std::min(part, n - off)); });
+    const size_t len = std::min(part, n - off);
+    try {
+      pool.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+    } catch (const std::system_error &) {
+      // no more threads to be had: this thread copies the rest itself
+      memcpy((char *)dst + off, (const char *)src + off, n - off);
+      break;
+    }
   }
-  memcpy(dst, src, std::min(part, n));
+  memcpy(dst, src, done_to);
   for (auto &th : pool) th.join();
 }
 
