@@ -480,8 +480,8 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   a.stages = stages;
   p->grid = std::min(a.nitems, slots);
   a.zwrap = u->decomposed ? 0 : 1;
-  if (u->decomposed && (kap->halo < 1 || u->halo < 1 || kap->z_off != u->z_off)) {
-    *why = "decomposed run needs one halo plane and matching z cuts of u and kap";
+  if (u->decomposed && (kap->halo < 1 || u->halo != kap->halo || kap->z_off != u->z_off)) {
+    *why = "decomposed run needs equal halo widths and matching z cuts of u and kap";
     delete p;
     return nullptr;
   }

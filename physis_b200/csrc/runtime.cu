@@ -115,7 +115,16 @@ Grid *GridSpace::Create(const __PSGridTypeInfo *ti, int num_dims, const int *dim
   g->nz_loc = dim[last];
   if (rt->world() > 1 && num_dims == 3) {
     g->decomposed = true;
-    g->halo = rt->opt.halo;
+    // halo width: the configured one (default 2, what the fused two-sweep pass needs), but never
+    // wider than the thinnest slab of this grid -- thin grids keep working with a one-plane halo
+    // (single sweeps only).  Computed from group-wide quantities, so every rank agrees.
+    int thinnest = dim[last];
+    for (int r = 0; r < rt->world(); ++r) {
+      int o_, l_;
+      PartitionGridZ(dim[last], rt->domain_dims[last], rt->world(), r, &o_, &l_);
+      thinnest = std::min(thinnest, l_);
+    }
+    g->halo = std::max(1, std::min(rt->opt.halo, thinnest));
     int lo_off;
     PartitionGridZ(dim[last], rt->domain_dims[last], rt->world(), rt->rank(), &g->z_off, &g->nz_loc);
     PartitionGridZ(dim[last], rt->domain_dims[last], rt->world(), rt->comm->lo(), &lo_off,
