@@ -116,8 +116,9 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     int stage = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-      const int zci = item / tiles_xy;
-      const int txy = item - zci * tiles_xy;
+      const int zseq = item / tiles_xy;
+      const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
+      const int txy = item - zseq * tiles_xy;
       const int ty = txy / a.ntx;
       const int tx = txy - ty * a.ntx;
       const int x0 = a.xbase + tx * G::TXB;
@@ -145,8 +146,9 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
   };
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-    const int zci = item / tiles_xy;
-    const int txy = item - zci * tiles_xy;
+    const int zseq = item / tiles_xy;
+    const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
+    const int txy = item - zseq * tiles_xy;
     const int ty = txy / a.ntx;
     const int tx = txy - ty * a.ntx;
     const int x = a.xbase + tx * G::TXB + lane * VEC;
@@ -269,6 +271,7 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     // the next item's first plane follows `sc` in the ring
     stage = next_of(sc);
     phase = (stage == 0) ? (phc ^ 1u) : phc;
+    SlabSyncItemDone(a.sync, item, NW * 32, threadIdx.x == 0);
   }
   SlabSyncSignal(a.sync, NW * 32, threadIdx.x == 0);
 }
@@ -387,7 +390,10 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
     a.push_lo_z = g[1]->halo;
     a.push_hi_z = g[1]->halo + g[1]->nz_loc - 1;
     p->pushes = true;
-    if (rt->FillSlabSync(&a.sync)) p->syncs = true;
+    if (rt->FillSlabSync(&a.sync)) {
+      p->syncs = true;
+      a.sync.boundary_items = rt->opt.early_signal ? std::min(a.nzc, 2) * a.ntx * a.nty : 0;
+    }
   }
 
   int dimv[3] = {nx, ny, nz};

@@ -130,8 +130,9 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
     tma::prefetch_tensormap(&map_kap);
     uint32_t epar = 0;  // bit s: parity of the next "slot s is free" phase to wait for
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-      const int zci = item / tiles_xy;
-      const int txy = item - zci * tiles_xy;
+      const int zseq = item / tiles_xy;
+      const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
+      const int txy = item - zseq * tiles_xy;
       const int ty = txy / a.ntx;
       const int tx = txy - ty * a.ntx;
       const int x0 = tx * (NBX * G::TXB);
@@ -278,8 +279,9 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
   const bool pushing = (a.push_lo_z >= 0) || (a.push_hi_z >= 0);
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-    const int zci = item / tiles_xy;
-    const int txy = item - zci * tiles_xy;
+    const int zseq = item / tiles_xy;
+    const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
+    const int txy = item - zseq * tiles_xy;
     const int ty = txy / a.ntx;
     const int tx = txy - ty * a.ntx;
     const int bx0 = tx * (NBX * G::TXB) + bx * G::TXB;
@@ -348,6 +350,7 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
         if (++z >= ze) { PS_RELEASE(1); break; }
       }
     }
+    SlabSyncItemDone(a.sync, item, NW * 32, threadIdx.x == 0);
   }
   SlabSyncSignal(a.sync, NW * 32, threadIdx.x == 0);
 #undef PS_STEP
@@ -491,7 +494,10 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
     a.push_lo_z = u->halo;
     a.push_hi_z = u->halo + u->nz_loc - 1;
     p->pushes = true;
-    if (rt->FillSlabSync(&a.sync)) p->syncs = true;
+    if (rt->FillSlabSync(&a.sync)) {
+      p->syncs = true;
+      a.sync.boundary_items = rt->opt.early_signal ? std::min(a.nzc, 2) * a.ntx * a.nty : 0;
+    }
   }
 
   int dimv[3] = {nx, ny, nz};

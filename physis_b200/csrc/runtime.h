@@ -151,6 +151,8 @@ struct Options {
                          //    the neighbour's halo (fused); 0: peer copies after the kernel
   int sync_mode = 2;     // 2: waits and signals fused into the sweep kernels, 0: stream
                          //    memory operations, 1: one-thread signal/wait kernels
+  int early_signal = 1;  // with sync_mode 2: publish a sweep's number as soon as its boundary z chunks
+                         // are done, so that the neighbours' next sweep overlaps the interior chunks
   int copyout_gather = 1;  // PSGridCopyout fills the whole host array on every rank
 };
 

@@ -318,8 +318,9 @@ Star7KernelV2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-      const int zci = item / tiles_xy;
-      const int txy = item - zci * tiles_xy;
+      const int zseq = item / tiles_xy;
+      const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
+      const int txy = item - zseq * tiles_xy;
       const int ty = txy / a.ntx;
       const int tx = txy - ty * a.ntx;
       const int x0 = a.xbase + tx * (NBX * G::TXB);
@@ -371,8 +372,9 @@ Star7KernelV2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
   } while (0)
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-    const int zci = item / tiles_xy;
-    const int txy = item - zci * tiles_xy;
+    const int zseq = item / tiles_xy;
+    const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
+    const int txy = item - zseq * tiles_xy;
     const int ty = txy / a.ntx;
     const int tx = txy - ty * a.ntx;
     const int x = a.xbase + tx * (NBX * G::TXB) + bx * G::TXB + lane * VEC;
@@ -466,6 +468,7 @@ Star7KernelV2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       if (z >= ze) break;
     }
     if (has_top) S7_RELEASE(stage_c);  // plane ze was loaded as the top plane only
+    SlabSyncItemDone(a.sync, item, NW * 32, threadIdx.x == 0);
   }
   SlabSyncSignal(a.sync, NW * 32, threadIdx.x == 0);
 #undef S7_STEP
@@ -683,7 +686,10 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
       a->push_hi_z = gout->halo + gout->nz_loc - 1;
       p->pushes = true;
       // the halo stores are in the kernel, so its ordering with the neighbours can be too
-      if (o.star7_impl != 0 && rt->FillSlabSync(&a->sync)) p->syncs = true;
+      if (o.star7_impl != 0 && rt->FillSlabSync(&a->sync)) {
+        p->syncs = true;
+        a->sync.boundary_items = o.early_signal ? std::min(nzc, 2) * ntx * nty : 0;
+      }
     }
   };
   if (dbl) { FillArgs(&p->ad, d, gin, gout); common(&p->ad); }

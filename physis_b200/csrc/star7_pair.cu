@@ -349,8 +349,9 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   } while (0)
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-    const int zci = item / a.nty;
-    const int ty = item - zci * a.nty;
+    const int zseq = item / a.nty;
+    const int zci = SLAB ? SlabChunkOrder(a.sync, zseq, a.nzc) : zseq;
+    const int ty = item - zseq * a.nty;
     const int zb = a.dz0 + zci * a.zc;
     const int ze = min(zb + a.zc, a.dz1);
     const int k0 = (zb == a.zface_lo) ? zb - 1 : zb - 2;  // first plane of the input window
@@ -406,6 +407,7 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         if (++k >= ze) break;
       }
     }
+    if (SLAB) SlabSyncItemDone(a.sync, item, PG::THREADS, threadIdx.x == 0);
   }
   if (SLAB) SlabSyncSignal(a.sync, PG::THREADS, threadIdx.x == 0);
 #undef SP_STEP
@@ -588,6 +590,7 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
       a->push_lo_z = a->push_hi_z = -(1 << 30);
       a->push_lo_delta = a->push_hi_delta = 0;
       a->sync = sync;
+      if (multi) a->sync.boundary_items = o.early_signal ? std::min(nzc, 2) * nty : 0;
       if (multi) {
         const Grid *go = gout[dir];
         const MemberLayout &ml = go->members[0];

@@ -58,7 +58,19 @@ struct SlabSync {
   unsigned *done;          // CTAs of this launch that have finished (self-resetting)
   uint32_t wait_epoch;     // neighbours must have completed this many sweeps
   uint32_t signal_epoch;   // the number this sweep publishes
+  // Overlap of the exchange with interior compute: work items are ordered so that the z chunks
+  // touching the slab's two ends come first (SlabChunkOrder); once these `boundary_items`
+  // items are done -- the halo planes the neighbours wait for are delivered and this rank's own
+  // halo planes are no longer read -- the sweep publishes its number, and the rest of the sweep
+  // (the interior chunks) runs while the signal travels.  0: publish when the whole sweep is done.
+  int boundary_items;
 };
+
+// z chunk a work item with chunk sequence number `seq` processes: 0, nzc-1, 1, 2, ..., nzc-2
+__device__ __forceinline__ int SlabChunkOrder(const SlabSync &s, int seq, int nzc) {
+  if (s.boundary_items == 0 || nzc < 3) return seq;
+  return seq == 0 ? 0 : (seq == 1 ? nzc - 1 : seq - 1);
+}
 
 __device__ __forceinline__ uint32_t LdAcquireSys(const uint32_t *p) {
   uint32_t v;
@@ -81,10 +93,28 @@ __device__ __forceinline__ void SlabSyncWait(const SlabSync &s) {
   }
 }
 
+// Called by every consumer thread of a CTA after it has finished work item `item`: the last
+// of the boundary items to finish publishes the sweep's number to both neighbours.
+__device__ __forceinline__ void SlabSyncItemDone(const SlabSync &s, int item, int nthreads, bool leader) {
+  if (!s.done || item >= s.boundary_items) return;
+  __threadfence_system();  // this thread's stores (incl. peer stores) are visible system-wide
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+  if (leader) {
+    const unsigned prev = atomicAdd(s.done, 1u);
+    if (prev == (unsigned)s.boundary_items - 1u) {
+      *s.done = 0;           // next launch starts from zero (stream order)
+      __threadfence_system();
+      StReleaseSys(s.to_lo, s.signal_epoch);
+      StReleaseSys(s.to_hi, s.signal_epoch);
+    }
+  }
+}
+
 // Called by every consumer thread after its last store; `nthreads` consumer threads
-// take part (a multiple of 32), `leader` is true for exactly one of them.
+// take part (a multiple of 32), `leader` is true for exactly one of them.  (With boundary
+// items the number has already been published by SlabSyncItemDone.)
 __device__ __forceinline__ void SlabSyncSignal(const SlabSync &s, int nthreads, bool leader) {
-  if (!s.done) return;
+  if (!s.done || s.boundary_items > 0) return;
   __threadfence_system();  // this thread's stores (incl. peer stores) are visible system-wide
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
   if (leader) {
