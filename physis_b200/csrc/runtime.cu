@@ -474,7 +474,6 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "stage_chunk_mb") o->stage_chunk = (size_t)val << 20;
   else if (k == "copy_threads") o->copy_threads = (int)val;
   else if (k == "early_signal") o->early_signal = (int)val;
-  else if (k == "tma_l2promo") g_tma_l2_promotion = (int)val;
   else return -1;
   return 0;
 }

@@ -8,17 +8,7 @@
 
 namespace physis_b200 {
 
-int g_tma_l2_promotion = 3;  // 0 none, 1 64 B, 2 128 B, 3 256 B (option tma_l2promo)
-
 namespace {
-CUtensorMapL2promotion Promo() {
-  switch (g_tma_l2_promotion) {
-    case 0: return CU_TENSOR_MAP_L2_PROMOTION_NONE;
-    case 1: return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
-    case 2: return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-    default: return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-  }
-}
 using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                               const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                               const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -53,7 +43,7 @@ bool EncodeTensorMap3D(CUtensorMap *out, TmaElem elem, const void *base, const i
   CUresult r = ResolveEncode()(
       out, elem == TmaElem::F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
       3, const_cast<void *>(base), gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-      CU_TENSOR_MAP_SWIZZLE_NONE, Promo(),
+      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -73,7 +63,7 @@ bool EncodeTensorMap2D(CUtensorMap *out, TmaElem elem, const void *base, const i
   CUresult r = ResolveEncode()(
       out, elem == TmaElem::F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
       2, const_cast<void *>(base), gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-      CU_TENSOR_MAP_SWIZZLE_NONE, Promo(),
+      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -89,7 +79,7 @@ bool EncodeTensorMap1D(CUtensorMap *out, TmaElem elem, const void *base, size_t 
   CUresult r = ResolveEncode()(
       out, elem == TmaElem::F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
       1, const_cast<void *>(base), gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-      CU_TENSOR_MAP_SWIZZLE_NONE, Promo(),
+      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }

@@ -143,7 +143,6 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
 // Host side: cuTensorMapEncodeTiled through the runtime's driver entry point
 // lookup (no link-time dependency on libcuda).
 enum class TmaElem { F32, F64 };
-extern int g_tma_l2_promotion;  // L2 promotion of every tensor map encoded from now on (tuning)
 // Describes a dense 3-D array (x fastest) of `dim` elements and a box of
 // `box` elements; returns false if the shape violates a TMA constraint
 // (16-byte strides/alignment, box <= 256 per dim).
