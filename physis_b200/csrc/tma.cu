@@ -68,20 +68,4 @@ bool EncodeTensorMap2D(CUtensorMap *out, TmaElem elem, const void *base, const i
   return r == CUDA_SUCCESS;
 }
 
-bool EncodeTensorMap1D(CUtensorMap *out, TmaElem elem, const void *base, size_t n, int box) {
-  const size_t es = elem == TmaElem::F64 ? 8 : 4;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
-  if (n == 0 || n >= (1ull << 31) || box < 1 || box > 256 || ((size_t)box * es) % 16 != 0) return false;
-  cuuint64_t gdim[1] = {(cuuint64_t)n};
-  cuuint64_t gstride[1] = {0};  // unused for rank 1
-  cuuint32_t bdim[1] = {(cuuint32_t)box};
-  cuuint32_t estr[1] = {1};
-  CUresult r = ResolveEncode()(
-      out, elem == TmaElem::F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-      1, const_cast<void *>(base), gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
 }  // namespace physis_b200

@@ -94,17 +94,8 @@ __device__ __forceinline__ void load_3d(void *smem_dst, const CUtensorMap *m, ui
       : "memory");
 }
 
-// 1-D tiled load: `box` consecutive elements starting at element c0 of a flat array.  The
-// start coordinate is arbitrary (only the array base must be 16-byte aligned), which is what
-// makes rows of an array whose pitch is not a multiple of 16 bytes loadable by TMA.
-__device__ __forceinline__ void load_1d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0) {
-  asm volatile(
-      "cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0)
-      : "memory");
-}
-
+// 2-D tiled load.  (A box must start on a 16-byte boundary in global memory: a 1-D or 2-D box
+// starting at an odd fp64 element raises an illegal-instruction error, tools/microbench/tma1d_test.cu.)
 __device__ __forceinline__ void load_2d(void *smem_dst, const CUtensorMap *m, uint64_t *bar,
                                         int c0, int c1) {
   asm volatile(
@@ -151,7 +142,5 @@ bool EncodeTensorMap3D(CUtensorMap *out, TmaElem elem, const void *base, const i
 // Dense 2-D array (x fastest) of `dim` elements read in boxes of `box` elements.
 bool EncodeTensorMap2D(CUtensorMap *out, TmaElem elem, const void *base, const int dim[2],
                        const int box[2]);
-// Flat array of `n` elements (n < 2^31) read in boxes of `box` elements.
-bool EncodeTensorMap1D(CUtensorMap *out, TmaElem elem, const void *base, size_t n, int box);
 
 }  // namespace physis_b200
