@@ -2,7 +2,7 @@
  * Hand-emitted `b200`-target translation of this repo's
  *   examples/dsl/diffusion3d_periodic_staggered.c   (BASELINE config 5)
  * User type `struct Cell {double p, q;}`: SoA on the device, so the generic
- * kernels see `struct __PSGrid3DCell_dev { int dim[3]; double *p; double *q; }`
+ * kernels see `struct __PSGrid3DCell_dev { int dim[3]; int slab; double *p; double *q; }`
  * (the layout translator/cuda_runtime_builder.cc:351-391 generates), which
  * overlays the runtime's device view.  Entry points match
  * oracle/programs/diffusion3d_periodic_staggered.ref.c.
@@ -17,6 +17,7 @@ struct Cell {
 };
 struct __PSGrid3DCell_dev {
   int dim[3];
+  int slab;
   double *p;
   double *q;
 };

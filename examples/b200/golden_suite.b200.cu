@@ -11,7 +11,7 @@
 #include "physis/physis_b200_generic.cuh"
 
 /* by-value device views (layout of Grid::dev_view): dims, then one pointer per member */
-struct GV3 { int dim[3]; void *m[4]; };
+struct GV3 { int dim[3]; int slab; void *m[4]; };
 struct GV1 { int dim[1]; void *m[1]; };
 struct GV2 { int dim[2]; void *m[1]; };
 static GV3 MakeGV3(const __PSGrid *g, int nmembers) {
@@ -44,8 +44,15 @@ static GV1 MakeGV1(const __PSGrid *g) {
 #define KG2 const GV2 *
 #define GET(T, g, off) (((T *)((g)->m[0]))[off])
 #define GETM(ST, T, g, m_, mi, ci, off) \
-  (((T *)((g)->m[mi]))[(size_t)(ci) * ((size_t)(g)->dim[0] * (g)->dim[1] * (g)->dim[2]) + (off)])
+  (((T *)((g)->m[mi]))[(size_t)(ci) * __PSGridMemberStride3DDev(g) + (off)])
 #define GRID_NEW(ti, nd, dims) __PSGridNew(ti, nd, dims, NULL)
+
+/* largest |z offset| of a kernel's reads where it exceeds one plane (from the translator's
+ * StencilRange): a multi-GPU run checks it against the halo width */
+template <typename S> struct ZReachOf { static constexpr int v = 0; };
+#define STENCIL_ZREACH(K, R)   \
+  struct __PSStencil_##K;      \
+  template <> struct ZReachOf<__PSStencil_##K> { static constexpr int v = R; };
 
 #define B200_DESCRIBE(K, NG, ...)                                                               \
   static void __PSStencilDescribe_##K(const struct __PSStencil_##K *s, __PSB200StencilDesc *d) { \
@@ -58,6 +65,7 @@ static GV1 MakeGV1(const __PSGrid *g) {
     d->stencil = s;                                                                             \
     d->launch = __PSStencilLaunch_##K;                                                          \
     d->name = #K;                                                                               \
+    d->z_reach = ZReachOf<__PSStencil_##K>::v;                                                  \
   }
 
 #define DEF_STENCIL_1U(K, NM)                                                                   \

@@ -249,6 +249,24 @@ float himeno_jacobi_gosa(int nn) {
   return gosa;
 }
 
+/* the original benchmark's structure (himenobmtxpa_original.c:299-346): a residual every
+ * iteration -- every PSStencilRun of the ping-pong pair is followed by its PSReduce */
+float himeno_jacobi_gosa_each(int nn) {
+  float gosa = 0.0f;
+  __PSGrid *p0 = G[P0], *p1 = G[P1];
+  PSDomain3D innerDom = PSDomain3DNew(1, PSGridDim(p0, 0) - 1,
+                                      1, PSGridDim(p0, 1) - 1,
+                                      1, PSGridDim(p0, 2) - 1);
+  assert(nn % 2 == 0);
+  for (int n = 0; n < nn / 2; ++n) {
+    __PSStencilRun_0(1, __PSStencilMap_jacobi_kernel(innerDom, p0, p1, G[GOSA], omega),
+                     __PSStencilMap_jacobi_kernel(innerDom, p1, p0, G[GOSA], omega),
+                     g_force_generic);
+    __PSReduceGridFloat(&gosa, PS_SUM, G[GOSA]);
+  }
+  return gosa;
+}
+
 /* bench hook: sweeps only (no reduction), returns nothing */
 void himeno_sweeps_only(int nn, int with_gosa) {
   __PSGrid *p0 = G[P0], *p1 = G[P1];

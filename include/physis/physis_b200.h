@@ -108,17 +108,28 @@ PSDomain3D PSDomain3DNew(PSIndex minx, PSIndex maxx, PSIndex miny, PSIndex maxy,
  * Primitive grids: dim[] then one pointer.  User types are stored SoA on the
  * device (as the reference CUDA target does, cuda_runtime_builder.cc:351-391):
  * dim[] followed by one pointer per struct member, in declaration order, so a
- * generated `struct __PSGrid3D<Name>_dev { int dim[3]; T0 *m0; T1 *m1; }`
- * overlays it exactly. */
+ * generated `struct __PSGrid3D<Name>_dev { int dim[3]; int slab; T0 *m0; T1 *m1; }`
+ * overlays it exactly.
+ *
+ * 3-D views carry `slab` in the four bytes the CUDA target's struct leaves as padding
+ * before its first pointer (same offsets of dim[] and p): 0 when the grid lives whole on
+ * this GPU, else the number of z planes of this rank's allocation (interior + halo).  On a
+ * z-slab the view's pointers are shifted so that GLOBAL plane indices address the local
+ * allocation, and the periodic wrap in z is not a modulo but the halo planes themselves
+ * (the ring exchange fills rank 0's lower halo with the last plane and vice versa) -- the
+ * role of local_size/local_offset in the MPI-CUDA target's device structs
+ * (include/physis/physis_mpi_cuda.h:53-94) and of GridMPI's periodic handling
+ * (runtime/grid_mpi.h:213-232). */
 typedef struct { int dim[1]; void *p; } __PSGrid1D_dev;
 typedef struct { int dim[2]; void *p; } __PSGrid2D_dev;
-typedef struct { int dim[3]; void *p; } __PSGrid3D_dev;
-typedef struct { int dim[3]; void *p; } __PSGrid_dev;
+typedef struct { int dim[3]; int slab; void *p; } __PSGrid3D_dev;
+typedef struct { int dim[3]; int slab; void *p; } __PSGrid_dev;
 #define __PS_DECL_DEV(N, Name, T) typedef struct { int dim[N]; T *p; } __PSGrid##N##D##Name##_dev;
-__PS_DECL_DEV(1, Float, float)  __PS_DECL_DEV(2, Float, float)  __PS_DECL_DEV(3, Float, float)
-__PS_DECL_DEV(1, Double, double) __PS_DECL_DEV(2, Double, double) __PS_DECL_DEV(3, Double, double)
-__PS_DECL_DEV(1, Int, int)      __PS_DECL_DEV(2, Int, int)      __PS_DECL_DEV(3, Int, int)
-__PS_DECL_DEV(1, Long, long)    __PS_DECL_DEV(2, Long, long)    __PS_DECL_DEV(3, Long, long)
+#define __PS_DECL_DEV3(Name, T) typedef struct { int dim[3]; int slab; T *p; } __PSGrid3D##Name##_dev;
+__PS_DECL_DEV(1, Float, float)  __PS_DECL_DEV(2, Float, float)  __PS_DECL_DEV3(Float, float)
+__PS_DECL_DEV(1, Double, double) __PS_DECL_DEV(2, Double, double) __PS_DECL_DEV3(Double, double)
+__PS_DECL_DEV(1, Int, int)      __PS_DECL_DEV(2, Int, int)      __PS_DECL_DEV3(Int, int)
+__PS_DECL_DEV(1, Long, long)    __PS_DECL_DEV(2, Long, long)    __PS_DECL_DEV3(Long, long)
 
 /* Host handle; field order and types as the CUDA target's so `g->dim[d]`,
  * `g->dev` in translated host code keep working. */
@@ -222,12 +233,21 @@ PS_FUNCTION_DEVICE static inline PSIndex __PSGridGetOffsetPeriodic2DDev(const vo
   return __PSGridGetOffsetPeriodic1DDev(g, i1) +
          (i2 + __PS_DEVDIM(g, 1)) % __PS_DEVDIM(g, 1) * __PS_DEVDIM(g, 0);
 }
+#define __PS_DEVSLAB(g) (((const __PSGrid_dev *)(g))->slab)
 PS_FUNCTION_DEVICE static inline PSIndex __PSGridGetOffsetPeriodic3DDev(const void *g,
                                                                         PSIndex i1,
                                                                         PSIndex i2,
                                                                         PSIndex i3) {
-  return __PSGridGetOffsetPeriodic2DDev(g, i1, i2) +
-         (i3 + __PS_DEVDIM(g, 2)) % __PS_DEVDIM(g, 2) * __PS_DEVDIM(g, 0) * __PS_DEVDIM(g, 1);
+  /* on a z-slab planes -1 and dim[2] are this rank's halo planes (ring wrap) */
+  const PSIndex z = __PS_DEVSLAB(g) ? i3 : (i3 + __PS_DEVDIM(g, 2)) % __PS_DEVDIM(g, 2);
+  return __PSGridGetOffsetPeriodic2DDev(g, i1, i2) + z * __PS_DEVDIM(g, 0) * __PS_DEVDIM(g, 1);
+}
+/* Elements between consecutive components of an array member of a user type (device SoA,
+ * components plane-major as translator/cuda_runtime_builder.cc:267-305 indexes them): the
+ * number of elements of this rank's allocation. */
+PS_FUNCTION_DEVICE static inline size_t __PSGridMemberStride3DDev(const void *g) {
+  return (size_t)__PS_DEVDIM(g, 0) * (size_t)__PS_DEVDIM(g, 1) *
+         (size_t)(__PS_DEVSLAB(g) ? __PS_DEVSLAB(g) : __PS_DEVDIM(g, 2));
 }
 
 /* ---- b200 stencil-run entry (NEW) -------------------------------------- */
@@ -279,6 +299,11 @@ typedef struct {
   const char *name;                  /* kernel name for --physis-trace */
   unsigned written_mask;             /* GENERIC: bit i set = grids[i] is PSGridEmit'ed (multi-GPU
                                       * halo refresh); 0 = unknown, refresh every grid */
+  int z_reach;                       /* GENERIC: largest |z offset| of any PSGridGet in the kernel
+                                      * (the translator's StencilRange; the reference sizes its halos
+                                      * from it, runtime/grid_space_mpi.h:42-62).  A multi-GPU run
+                                      * refuses a sweep that reaches beyond the halo planes (option
+                                      * `halo`); 0 = not stated, at most one plane assumed */
 } __PSB200StencilDesc;
 
 /* for (i < iter) { sweep descs[0]; sweep descs[1]; ... } enqueued in order on
@@ -310,6 +335,8 @@ typedef struct {
   uint64_t fused_pairs;   /* of kernel_launches: fused two-sweep passes (two sweeps each) */
   uint64_t fused_pairs_timed; /* with option time_kernels=1: passes covered by fused_pair_ms */
   double fused_pair_ms;       /* ... and their accumulated device time (CUDA events) */
+  uint64_t reduces_from_partials; /* PSReduce calls answered from the partial sums the producing
+                                   * sweep left behind instead of a pass over the grid */
 } __PSB200Stats;
 void __PSB200GetStats(__PSB200Stats *out);
 void __PSB200ResetStats(void);

@@ -12,6 +12,7 @@
 
 #define GOLDEN_EXPORT
 #define GK static inline
+#define STENCIL_ZREACH(K, R)   /* b200-target hint (halo width); nothing on the REF target */
 #define KG __PSGrid *
 #define KG1 __PSGrid *
 #define KGU __PSGrid *

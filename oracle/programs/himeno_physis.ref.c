@@ -279,3 +279,28 @@ float himeno_jacobi_gosa(int nn) {
   __PSReduceGridFloat(&gosa, PS_SUM, G[GOSA]);
   return gosa;
 }
+
+/* the original benchmark's structure (himenobmtxpa_original.c:299-346): a residual every
+ * iteration -- here every PSStencilRun of the ping-pong pair is followed by its PSReduce */
+float himeno_jacobi_gosa_each(int nn) {
+  float gosa = 0.0f;
+  __PSGrid *p0 = G[P0], *p1 = G[P1];
+  PSDomain3D innerDom = PSDomain3DNew(1, PSGridDim(p0, 0) - 1,
+                                      1, PSGridDim(p0, 1) - 1,
+                                      1, PSGridDim(p0, 2) - 1);
+  assert(nn % 2 == 0);
+  struct __PSStencil_jacobi_kernel_gosa s0 = {
+      __PSStencilMap_jacobi_kernel(innerDom, p0, p1, G[A0], G[A1], G[A2], G[A3],
+                                   G[B0], G[B1], G[B2], G[C0], G[C1], G[C2],
+                                   G[BND], G[WRK1], omega),
+      G[GOSA], __PSGridGetID(G[GOSA])};
+  struct __PSStencil_jacobi_kernel_gosa s1 = s0;
+  s1.base.p0 = p1;
+  s1.base.p1 = p0;
+  int n;
+  for (n = 0; n < nn / 2; ++n) {
+    __PSStencilRun_1(1, s0, s1);
+    __PSReduceGridFloat(&gosa, PS_SUM, G[GOSA]);
+  }
+  return gosa;
+}

@@ -45,14 +45,16 @@ class StencilDesc(C.Structure):
                 ("num_grids", C.c_int), ("grids", C.c_void_p * MAX_GRIDS),
                 ("members", C.c_int * MAX_GRIDS), ("num_scalars", C.c_int),
                 ("scalars", C.c_double * MAX_SCALARS), ("stencil", C.c_void_p),
-                ("launch", C.c_void_p), ("name", C.c_char_p), ("written_mask", C.c_uint)]
+                ("launch", C.c_void_p), ("name", C.c_char_p), ("written_mask", C.c_uint),
+                ("z_reach", C.c_int)]
 
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("halo_bytes", C.c_uint64),
                 ("last_kernel_ms", C.c_float), ("fused_pairs", C.c_uint64),
-                ("fused_pairs_timed", C.c_uint64), ("fused_pair_ms", C.c_double)]
+                ("fused_pairs_timed", C.c_uint64), ("fused_pair_ms", C.c_double),
+                ("reduces_from_partials", C.c_uint64)]
 
 
 # every extern "C" symbol include/physis/physis_b200.h declares

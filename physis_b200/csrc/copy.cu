@@ -21,6 +21,7 @@ constexpr int kThreads = 256;
 struct MemberTable {
   int n;
   int elm_size;
+  int padded;   // the struct has padding bytes (no member covers them)
   void *dev[kMaxMembers];
   int offset[kMaxMembers];
   int size[kMaxMembers];
@@ -56,6 +57,12 @@ TransposeKernel(char *aos, const __grid_constant__ MemberTable tbl, long num_elm
       } else {
         for (int i = threadIdx.x; i < nbytes; i += kThreads) tile[i] = aos[byte0 + i];
       }
+      __syncthreads();
+    } else if (tbl.padded) {
+      // padding bytes belong to no member: they leave the device as zeros (what a fresh
+      // REFERENCE-target grid holds, runtime/libphysis_rt_ref.cc:53-71), never as stale
+      // shared memory
+      for (int i = threadIdx.x; i < (nbytes + 3) / 4; i += kThreads) reinterpret_cast<unsigned *>(tile)[i] = 0u;
       __syncthreads();
     }
     for (int m = 0; m < tbl.n; ++m) {
@@ -97,6 +104,7 @@ void Launch(const Grid &g, char *aos, bool to_soa, cudaStream_t s) {
   MemberTable tbl;
   tbl.n = (int)g.members.size();
   tbl.elm_size = g.elm_size;
+  int covered = 0;
   for (int m = 0; m < tbl.n; ++m) {
     const MemberLayout &ml = g.members[m];
     PSB_CHECK(ml.size == 4 || ml.size == 8, "struct members must be 4- or 8-byte scalars");
@@ -104,7 +112,9 @@ void Launch(const Grid &g, char *aos, bool to_soa, cudaStream_t s) {
     tbl.offset[m] = ml.aos_offset;
     tbl.size[m] = ml.size;
     tbl.count[m] = ml.count;
+    covered += ml.size * ml.count;
   }
+  tbl.padded = covered < g.elm_size ? 1 : 0;
   // tile: as many structs as fit 32 KiB, multiple of 16 so tiles stay 16-byte aligned
   int tile_elems = (32 * 1024) / g.elm_size;
   tile_elems = tile_elems / 16 * 16;

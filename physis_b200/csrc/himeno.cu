@@ -39,6 +39,10 @@ struct HimenoArgs {
   const float *a0, *a1, *a2, *a3, *b0, *b1, *b2, *c0, *c1, *c2, *bnd, *wrk1;
   float *p1;
   float *gosa;  // nullptr unless the _GOSA form
+  // _GOSA form: one partial sum per CTA of everything the launch emitted into `gosa`, so that
+  // the PSReduce(PS_SUM) which follows folds gridDim.x numbers instead of re-reading the grid
+  // (the original benchmark accumulates gosa inside the sweep: himenobmtxpa_original.c:334)
+  double *gosa_partials;
   float omega;
   int nx, ny, nz;
   int dx0, dx1, dy0, dy1, dz0, dz1;
@@ -145,6 +149,11 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     if (lane == 0) tma::mbar_arrive(&empty[st]);
   };
 
+  // sum of the ss*ss values this thread emits: fp32 within a vector, fp64 across planes and
+  // work items (one DADD per four points is free next to the loads, and keeps the partial
+  // within an ulp of the exact sum whatever the order)
+  double gacc = 0.0;
+
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
     const int zseq = item / tiles_xy;
     const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
@@ -240,6 +249,11 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
           SetElem(o, j, v);
           SetElem(q, j, MulRn(ss, ss));
         }
+        if (GOSA) {
+          const float e0 = ok[0] ? q.x : 0.f, e1 = ok[1] ? q.y : 0.f;
+          const float e2 = ok[2] ? q.z : 0.f, e3 = ok[3] ? q.w : 0.f;
+          gacc += (double)AddRn(AddRn(e0, e1), AddRn(e2, e3));
+        }
         float *const push0 = (z == a.push_lo_z) ? a.push_lo : nullptr;
         float *const push1 = (z == a.push_hi_z) ? a.push_hi : nullptr;
         const size_t gp = (size_t)y * a.nx + x;  // offset inside one plane
@@ -272,6 +286,19 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     stage = next_of(sc);
     phase = (stage == 0) ? (phc ^ 1u) : phc;
     SlabSyncItemDone(a.sync, item, NW * 32, threadIdx.x == 0);
+  }
+  if (GOSA) {
+    // per-CTA partial in a fixed order: lanes by a shuffle tree, warps one after the other
+    __shared__ double warp_part[NW];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) gacc += __shfl_down_sync(0xffffffffu, gacc, d);
+    if (lane == 0) warp_part[warp] = gacc;
+    asm volatile("bar.sync 2, %0;" ::"r"(NW * 32) : "memory");  // consumers only: the producer has left
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < NW; ++w) t += warp_part[w];
+      a.gosa_partials[blockIdx.x] = t;
+    }
   }
   SlabSyncSignal(a.sync, NW * 32, threadIdx.x == 0);
 }
@@ -362,6 +389,7 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
   for (int i = 0; i < 12; ++i) *coef[i] = (const float *)g[2 + i]->members[0].dev;
   a.p1 = (float *)g[1]->members[0].dev;
   a.gosa = gosa ? (float *)g[14]->members[0].dev : nullptr;
+  a.gosa_partials = nullptr;
   a.omega = (float)d.scalars[0];
   a.nx = nx; a.ny = ny; a.nz = nz;
   a.dx0 = dom.local_min[0]; a.dx1 = dom.local_max[0];
@@ -384,6 +412,12 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
   a.nitems = a.ntx * a.nty * a.nzc;
   a.stages = stages;
   p->grid = std::min(a.nitems, slots);
+  if (gosa) {
+    Grid::SumCache &sc = g[14]->sum_cache;
+    if (!sc.partials) sc.partials = new DeviceBuffer();
+    sc.partials->EnsureCapacity(sizeof(double) * (size_t)slots, rt->stream);
+    a.gosa_partials = (double *)sc.partials->get();
+  }
   a.push_lo_z = a.push_hi_z = -1;
   a.sync = SlabSync{};
   if (SlabPushTargets(rt, *g[1], 0, (void **)&a.push_lo, (void **)&a.push_hi, sizeof(float))) {
@@ -392,7 +426,7 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
     p->pushes = true;
     if (rt->FillSlabSync(&a.sync)) {
       p->syncs = true;
-      a.sync.boundary_items = rt->opt.early_signal ? std::min(a.nzc, 2) * a.ntx * a.nty : 0;
+      SlabSyncSetBoundary(&a.sync, rt->opt.early_signal != 0, nzd, a.zc, a.nzc, a.ntx * a.nty, 1);
     }
   }
 
@@ -418,5 +452,6 @@ void LaunchHimeno(Runtime *rt, HimenoPlan *p) {
 void DestroyHimeno(HimenoPlan *p) { delete p; }
 bool HimenoPushes(const HimenoPlan *p) { return p->pushes; }
 bool HimenoSyncs(const HimenoPlan *p) { return p->syncs; }
+int HimenoPartialCount(const HimenoPlan *p) { return p->args.gosa_partials ? p->grid : 0; }
 
 }  // namespace physis_b200

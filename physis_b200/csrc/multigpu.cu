@@ -24,6 +24,7 @@
 //    the reference (runtime/grid_space_mpi.h:269-281).
 #include "runtime.h"
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -48,14 +49,9 @@ void ResolveMemOps() {
 }
 
 // Fallback when stream memory operations are unavailable: one-thread kernels.
-__global__ void WaitFlagsKernel(const volatile uint32_t *flags, uint32_t epoch) {
-  for (int i = 0; i < 2; ++i) {
-    uint32_t spins = 0;
-    while ((int32_t)(flags[i] - epoch) < 0) {
-      __nanosleep(100);
-      if (++spins > (1u << 28)) __trap();
-    }
-  }
+__global__ void WaitFlagsKernel(const uint32_t *flags, uint32_t epoch, unsigned long long timeout_ns,
+                                uint32_t *err) {
+  sweep::SlabWaitFlags(flags, epoch, timeout_ns, err);
   __threadfence_system();
 }
 __global__ void SignalFlagsKernel(uint32_t *to_lo, uint32_t *to_hi, uint32_t epoch) {
@@ -82,6 +78,10 @@ void Runtime::InitGroup() {
   if ((!g_wait32 || !g_write32) && opt.sync_mode == 0) opt.sync_mode = 1;
   sweep_epoch = 0;
   done_counter = reinterpret_cast<unsigned *>(flags + 16);  // same zeroed allocation
+  void *e = nullptr;
+  PSB_CUDA(cudaHostAlloc(&e, 64, cudaHostAllocMapped));
+  memset(e, 0, 64);
+  dev_err = static_cast<volatile uint32_t *>(e);
 }
 
 bool Runtime::FillSlabSync(sweep::SlabSync *s) {
@@ -91,6 +91,8 @@ bool Runtime::FillSlabSync(sweep::SlabSync *s) {
   s->to_lo = flags_of_lo + 1;  // this rank is the upper neighbour of `lo`
   s->to_hi = flags_of_hi + 0;
   s->done = done_counter;
+  s->timeout_ns = (unsigned long long)std::max(1, opt.sync_timeout_s) * 1000000000ull;
+  s->err = const_cast<uint32_t *>(dev_err);
   return true;
 }
 
@@ -101,9 +103,21 @@ void Runtime::ShutdownGroup() {
     if (flags_of_hi != flags_of_lo) CloseIpc(flags_of_hi);
     if (flags) cudaFree(flags);
     flags = flags_of_lo = flags_of_hi = nullptr;
+    if (dev_err) cudaFreeHost(const_cast<uint32_t *>(dev_err));
+    dev_err = nullptr;
   }
   delete comm;
   comm = nullptr;
+}
+
+void Runtime::CheckDeviceErrors(const char *where) {
+  if (!dev_err || dev_err[0] == 0) return;
+  fprintf(stderr,
+          "[physis-b200] rank %d (%s): the %s ring neighbour never published sweep %u (last seen %u, "
+          "CTA %u, waited %d s; option sync_timeout_s). Results are invalid.\n",
+          rank(), where, dev_err[0] == 1 ? "lower" : "upper", dev_err[1], dev_err[2], dev_err[3],
+          opt.sync_timeout_s);
+  exit(1);
 }
 
 void Runtime::ExchangeIpc(void *mine, void **of_lo, void **of_hi) {
@@ -132,7 +146,9 @@ void Runtime::WaitNeighbours(uint32_t epoch) {
       PSB_CHECK(r == CUDA_SUCCESS, "cuStreamWaitValue32 failed");
     }
   } else {
-    WaitFlagsKernel<<<1, 1, 0, stream>>>(flags, epoch);
+    WaitFlagsKernel<<<1, 1, 0, stream>>>(flags, epoch,
+                                         (unsigned long long)std::max(1, opt.sync_timeout_s) * 1000000000ull,
+                                         const_cast<uint32_t *>(dev_err));
     stats.kernel_launches++;
   }
 }

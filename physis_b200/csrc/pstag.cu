@@ -496,7 +496,7 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
     p->pushes = true;
     if (rt->FillSlabSync(&a.sync)) {
       p->syncs = true;
-      a.sync.boundary_items = rt->opt.early_signal ? std::min(a.nzc, 2) * a.ntx * a.nty : 0;
+      SlabSyncSetBoundary(&a.sync, rt->opt.early_signal != 0, nzd, a.zc, a.nzc, a.ntx * a.nty, 1);
     }
   }
 

@@ -20,6 +20,7 @@
 // only (tests bound it; exactly-representable data is bit-identical).
 #include "runtime.h"
 
+#include <type_traits>
 #include <vector>
 
 #include <cfloat>
@@ -146,6 +147,16 @@ ReduceStage2(const T *__restrict__ partials, int n, T *__restrict__ out) {
   if (threadIdx.x == 0) *out = acc;
 }
 
+// PSReduce(PS_SUM) right after the sweep that emitted the grid: the sweep left one fp64
+// partial per CTA (Grid::SumCache), folded here by one block in a fixed order.
+__global__ void __launch_bounds__(kThreads)
+FoldPartials(const double *__restrict__ partials, int n, float *__restrict__ out) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += kThreads) acc += partials[i];
+  acc = BlockFold<double, PS_SUM>(acc);
+  if (threadIdx.x == 0) *out = (float)acc;
+}
+
 template <typename T, int OP>
 void Run(Runtime *rt, const Grid &g, void *out_host) {
   // this rank's interior planes are contiguous in the local allocation
@@ -157,12 +168,25 @@ void Run(Runtime *rt, const Grid &g, void *out_host) {
   DeviceBuffer &scr = rt->small_scratch(sizeof(T) * (size_t)(blocks + 1));
   T *partials = (T *)scr.get();
   T *result = partials + blocks;
-  ReduceStage1<T, OP><<<blocks, kThreads, 0, rt->stream>>>(data, n, partials);
-  ReduceStage2<T, OP><<<1, kThreads, 0, rt->stream>>>(partials, blocks, result);
+  bool from_partials = false;
+  if constexpr (std::is_same<T, float>::value && OP == PS_SUM) {
+    if (g.sum_cache.valid && rt->opt.reduce_fuse) {
+      FoldPartials<<<1, kThreads, 0, rt->stream>>>((const double *)g.sum_cache.partials->get(),
+                                                  g.sum_cache.count, result);
+      rt->stats.kernel_launches += 1;
+      rt->stats.reduces_from_partials += 1;
+      from_partials = true;
+    }
+  }
+  if (!from_partials) {
+    ReduceStage1<T, OP><<<blocks, kThreads, 0, rt->stream>>>(data, n, partials);
+    ReduceStage2<T, OP><<<1, kThreads, 0, rt->stream>>>(partials, blocks, result);
+    rt->stats.kernel_launches += 2;
+  }
   PSB_CUDA(cudaGetLastError());
-  rt->stats.kernel_launches += 2;
   PSB_CUDA(cudaMemcpyAsync(out_host, result, sizeof(T), cudaMemcpyDeviceToHost, rt->stream));
   PSB_CUDA(cudaStreamSynchronize(rt->stream));
+  rt->CheckDeviceErrors("PSReduce");
   rt->stats.d2h_bytes += sizeof(T);
   if (g.decomposed) {
     // cross-GPU combine: one scalar per rank, folded in rank order on every rank

@@ -49,7 +49,7 @@ bool DeviceBuffer::Allocate(size_t bytes, cudaStream_t stream) {
 }
 
 void DeviceBuffer::EnsureCapacity(size_t bytes, cudaStream_t stream) {
-  if (bytes >= capacity_) {
+  if (bytes > capacity_) {
     if (ptr_) {
       // the old block may still be in use by work enqueued on `stream`
       PSB_CUDA(cudaStreamSynchronize(stream));
@@ -199,6 +199,7 @@ Grid *GridSpace::Create(const __PSGridTypeInfo *ti, int num_dims, const int *dim
   size_t view_bytes = ptr_off + sizeof(void *) * g->members.size();
   g->dev_view = calloc(1, view_bytes);
   for (int i = 0; i < num_dims; ++i) ((int *)g->dev_view)[i] = dim[i];
+  if (num_dims == 3) ((__PSGrid_dev *)g->dev_view)->slab = g->decomposed ? g->ldim[2] : 0;
   const int64_t shift = (int64_t)(g->z_off - g->halo) * g->plane_elms;
   for (size_t m = 0; m < g->members.size(); ++m)
     ((void **)((char *)g->dev_view + ptr_off))[m] =
@@ -224,6 +225,7 @@ void GridSpace::Destroy(Grid *g) {
     }
   }
   for (auto *s : g->storage) delete s;
+  delete g->sum_cache.partials;
   free(g->dev_view);
   delete g;
 }
@@ -474,6 +476,8 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "stage_chunk_mb") o->stage_chunk = (size_t)val << 20;
   else if (k == "copy_threads") o->copy_threads = (int)val;
   else if (k == "early_signal") o->early_signal = (int)val;
+  else if (k == "sync_timeout_s") o->sync_timeout_s = (int)val;
+  else if (k == "reduce_fuse") o->reduce_fuse = (int)val;
   else return -1;
   return 0;
 }
@@ -633,6 +637,7 @@ static void DownloadInterior(Runtime *rt, Grid *g, char *dst, int64_t dst_plane)
   }
   rt->CopyToHost(dst + (size_t)dst_plane * plane_bytes, src_base + (size_t)g->halo * plane_bytes,
                  (size_t)g->nz_loc * plane_bytes);
+  rt->CheckDeviceErrors("PSGridCopyout");
 }
 
 void __PSGridCopyin(void *gv, const void *src, __PSGrid_devCopyinFunc func) {
@@ -643,6 +648,7 @@ void __PSGridCopyin(void *gv, const void *src, __PSGrid_devCopyinFunc func) {
     return;
   }
   PSB_CHECK(!g->external_dev, "copyin of an externally allocated grid needs its helper");
+  g->NoteUnknownWrite();
   if (g->decomposed) {
     // every rank holds the same global host array (SPMD): take this rank's slab and
     // its halo planes straight from it -- no inter-GPU traffic.  The barrier makes
@@ -691,6 +697,7 @@ void __PSGridCopyout(void *gv, void *dst, __PSGrid_devCopyoutFunc func) {
 void __PSB200GridCopyinLocal(void *gv, const void *src) {
   Runtime *rt = Runtime::Get();
   Grid *g = Grid::FromHandle(gv);
+  g->NoteUnknownWrite();
   PSB_CUDA(cudaStreamSynchronize(rt->stream));
   if (g->decomposed) rt->comm->Barrier();
   SlabSeg seg = {0, g->halo, g->nz_loc};
@@ -761,6 +768,7 @@ void __PSGridSwap(__PSGrid *g) { (void)g; }
 void __PSGridSet(__PSGrid *gh, void *buf, ...) {
   Runtime *rt = Runtime::Get();
   Grid *g = Grid::FromHandle(gh);
+  g->NoteUnknownWrite();
   va_list vl;
   va_start(vl, buf);
   PSIndex idx[PS_MAX_DIM] = {0, 0, 0};
@@ -825,7 +833,11 @@ void __PSReduceGridLong(void *buf, enum PSReduceOp op, __PSGrid *g) {
 }
 
 __PSB200Stream __PSB200GetStream(void) { return (__PSB200Stream)Runtime::Get()->stream; }
-void __PSB200Synchronize(void) { PSB_CUDA(cudaStreamSynchronize(Runtime::Get()->stream)); }
+void __PSB200Synchronize(void) {
+  Runtime *rt = Runtime::Get();
+  PSB_CUDA(cudaStreamSynchronize(rt->stream));
+  rt->CheckDeviceErrors("__PSB200Synchronize");
+}
 
 void __PSB200TimerStart(void) {
   Runtime *rt = Runtime::Get();
@@ -836,6 +848,7 @@ float __PSB200TimerStopMs(void) {
   Runtime *rt = Runtime::Get();
   PSB_CUDA(cudaEventRecord(rt->timer_stop, rt->stream));
   PSB_CUDA(cudaEventSynchronize(rt->timer_stop));
+  rt->CheckDeviceErrors("__PSB200TimerStopMs");
   float ms = 0.f;
   PSB_CUDA(cudaEventElapsedTime(&ms, rt->timer_start, rt->timer_stop));
   return ms;

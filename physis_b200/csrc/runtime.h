@@ -25,9 +25,9 @@
 
 namespace physis_b200 {
 
-// Device allocation with grow-only capacity (semantics of Buffer::EnsureCapacity,
-// runtime/buffer.cc:22-35: reallocate when the request reaches the actual size,
-// otherwise only the logical size changes).  Fresh memory is zero-filled like
+// Device allocation with grow-only capacity (role of Buffer::EnsureCapacity,
+// runtime/buffer.cc:22-35, except that a repeated request of the same size keeps the
+// block: the reference's `>=` would re-allocate on every PSReduce / user-type copy).  Fresh memory is zero-filled like
 // BufferCUDADev (runtime/buffer_cuda.cu:106-117).
 class DeviceBuffer {
  public:
@@ -104,6 +104,37 @@ class Grid {
   void *dev_view = nullptr;            // host copy of the by-value device view
   bool external_dev = false;           // allocated by a generated devNew function
 
+  // PSReduce(PS_SUM) fused with the producing sweep: a sweep that emits this grid can leave
+  // per-CTA partial sums of what it emitted (himeno.cu, the residual form); a PSReduce that
+  // follows folds those few numbers instead of reading the grid back.  The partials stand for
+  // the whole grid only while everything outside the sweep's domain is still the zero fill of
+  // __PSGridNew, which is what the bookkeeping below establishes; any other write drops them.
+  struct SumCache {
+    bool valid = false;
+    int count = 0;              // partial sums (one per CTA of the producing launch)
+    DeviceBuffer *partials = nullptr;  // doubles
+  } sum_cache;
+  bool contents_unknown = false;       // written by the host or by a kernel the runtime cannot see into
+  bool emitted = false;                // some sweep has emitted into this grid ...
+  int emit_min[PS_MAX_DIM] = {0, 0, 0}, emit_max[PS_MAX_DIM] = {0, 0, 0};  // ... inside this box (global)
+  void NoteUnknownWrite() { sum_cache.valid = false; contents_unknown = true; }
+  void NoteEmit(const __PSDomain &dom) {
+    sum_cache.valid = false;
+    for (int i = 0; i < PS_MAX_DIM; ++i) {
+      emit_min[i] = emitted ? (dom.local_min[i] < emit_min[i] ? dom.local_min[i] : emit_min[i]) : dom.local_min[i];
+      emit_max[i] = emitted ? (dom.local_max[i] > emit_max[i] ? dom.local_max[i] : emit_max[i]) : dom.local_max[i];
+    }
+    emitted = true;
+  }
+  // true when every element outside `dom` still holds the zero fill
+  bool ZeroOutside(const __PSDomain &dom) const {
+    if (contents_unknown) return false;
+    if (!emitted) return true;
+    for (int i = 0; i < num_dims; ++i)
+      if (emit_min[i] < dom.local_min[i] || emit_max[i] > dom.local_max[i]) return false;
+    return true;
+  }
+
   bool is_user_type() const { return type == PS_USER; }
   size_t bytes() const { return (size_t)elm_size * (size_t)num_elms; }
   size_t alloc_bytes() const { return (size_t)elm_size * (size_t)n_alloc; }
@@ -154,6 +185,8 @@ struct Options {
   int early_signal = 1;  // with sync_mode 2: publish a sweep's number as soon as its boundary z chunks
                          // are done, so that the neighbours' next sweep overlaps the interior chunks
   int copyout_gather = 1;  // PSGridCopyout fills the whole host array on every rank
+  int sync_timeout_s = 120;  // a neighbour silent for longer than this is a reported error
+  int reduce_fuse = 1;   // PSReduce(PS_SUM) folds the partial sums the producing sweep left (himeno.cu)
 };
 
 class Runtime {
@@ -199,6 +232,11 @@ class Runtime {
   uint32_t *flags_of_hi = nullptr;
   uint32_t sweep_epoch = 0;          // sweeps enqueued so far (identical on every rank)
   unsigned *done_counter = nullptr;  // finished-CTA counter of sweeps that signal themselves
+  // host-mapped words a kernel writes when a neighbour's signal never arrives:
+  // [0] = 1 + neighbour (0 lo, 1 hi), [1] = sweep waited for, [2] = last value seen, [3] = CTA
+  volatile uint32_t *dev_err = nullptr;
+  // aborts with a message if a kernel reported a lost neighbour signal (call after a stream sync)
+  void CheckDeviceErrors(const char *where);
   // fills the device-side view of the flag words for a kernel that waits / signals itself;
   // false when the run is single-GPU or opt.sync_mode selects stream-ordered flags
   bool FillSlabSync(sweep::SlabSync *s);

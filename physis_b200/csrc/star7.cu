@@ -688,7 +688,7 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
       // the halo stores are in the kernel, so its ordering with the neighbours can be too
       if (o.star7_impl != 0 && rt->FillSlabSync(&a->sync)) {
         p->syncs = true;
-        a->sync.boundary_items = o.early_signal ? std::min(nzc, 2) * ntx * nty : 0;
+        SlabSyncSetBoundary(&a->sync, o.early_signal != 0, nzd, zc, nzc, ntx * nty, 1);
       }
     }
   };

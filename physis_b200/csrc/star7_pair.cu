@@ -63,14 +63,6 @@ struct PairArgs {
 
 constexpr int kPairSlots = 3;
 
-// out of line: the spin loop must not take part in the sweep's register allocation
-__device__ __noinline__ void PairWaitNeighbours(const uint32_t *flags, uint32_t epoch) {
-  SlabSync s{};
-  s.flags = flags;
-  s.wait_epoch = epoch;
-  SlabSyncWait(s);
-}
-
 template <typename T, int NBX, int NWY, int RY>
 struct PairGeom {
   static constexpr int H = NWY * RY;
@@ -115,7 +107,7 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     for (int s = 0; s < NS; ++s) tma::mbar_init(&full[s], 1);
     tma::fence_barrier_init();
     tma::prefetch_tensormap(&tmap);
-    if (SLAB) PairWaitNeighbours(a.sync.flags, a.sync.wait_epoch);  // before any halo plane is read or any peer halo written
+    if (SLAB) SlabSyncWait(a.sync);  // before any halo plane is read or any peer halo written
   }
 
   const int bx = warp % NBX;
@@ -590,7 +582,9 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
       a->push_lo_z = a->push_hi_z = -(1 << 30);
       a->push_lo_delta = a->push_hi_delta = 0;
       a->sync = sync;
-      if (multi) a->sync.boundary_items = o.early_signal ? std::min(nzc, 2) * nty : 0;
+      // every chunk that reads a halo plane or computes one of the two planes per side the
+      // neighbours receive finishes before the pass number is published
+      if (multi) SlabSyncSetBoundary(&a->sync, o.early_signal != 0, nz, zc, nzc, nty, 2);
       if (multi) {
         const Grid *go = gout[dir];
         const MemberLayout &ml = go->members[0];

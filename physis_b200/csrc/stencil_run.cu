@@ -31,6 +31,7 @@ void LaunchHimeno(Runtime *rt, HimenoPlan *p);
 void DestroyHimeno(HimenoPlan *p);
 bool HimenoPushes(const HimenoPlan *p);
 bool HimenoSyncs(const HimenoPlan *p);
+int HimenoPartialCount(const HimenoPlan *p);
 
 struct PstagPlan;
 PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *why);
@@ -53,6 +54,12 @@ struct SweepPlan {
   bool fused_sync = false;     // ... and orders itself with the neighbours (SlabSync)
   // (grid, member) pairs whose halo planes must reach the neighbours after the sweep
   std::vector<std::pair<Grid *, int>> written;
+  // bookkeeping of what the grids hold (Grid::SumCache): the sweep's domain in global
+  // coordinates, every grid it emits into, and the grid whose emitted values the kernel also
+  // sums up per CTA (the residual form of the Himeno sweep)
+  __PSDomain gdom;
+  std::vector<Grid *> outputs;
+  Grid *sum_grid = nullptr;
 };
 
 // Clips the z-range of a domain to this rank's slab.  Specialised kernels work on
@@ -90,6 +97,22 @@ SweepPlan *PrepareSweep(Runtime *rt, const __PSB200StencilDesc &d_in) {
   std::string why;
   Grid *g0 = d_in.num_grids > 0 ? Grid::FromHandle(d_in.grids[0]) : nullptr;
   const bool multi = rt->world() > 1;
+  p->gdom = d_in.dom;
+  switch (d_in.kind) {
+    case PSB200_KIND_DIFFUSION7_CLAMP:
+    case PSB200_KIND_HIMENO19:
+      if (d_in.num_grids > 1) p->outputs.push_back(Grid::FromHandle(d_in.grids[1]));
+      break;
+    case PSB200_KIND_HIMENO19_GOSA:
+      if (d_in.num_grids > 1) p->outputs.push_back(Grid::FromHandle(d_in.grids[1]));
+      if (d_in.num_grids > 14) p->sum_grid = Grid::FromHandle(d_in.grids[14]);
+      break;
+    case PSB200_KIND_PERIODIC7_STAGGERED:
+      if (g0) p->outputs.push_back(g0);
+      break;
+    default:
+      break;
+  }
   if (multi && d_in.kind != PSB200_KIND_GENERIC && g0) {
     __PSB200StencilDesc d = d_in;
     p->empty = !LocaliseDomain(g0, &d.dom, true);
@@ -162,12 +185,30 @@ SweepPlan *PrepareSweep(Runtime *rt, const __PSB200StencilDesc &d_in) {
     p->fused_push = false;
     p->fused_sync = false;
     p->written.clear();
+    // which grids a generated kernel emits into is only known to the translator (written_mask)
+    p->outputs.clear();
+    p->sum_grid = nullptr;
+    for (int i = 0; i < d_in.num_grids; ++i)
+      if (!d_in.written_mask || (d_in.written_mask & (1u << i))) p->outputs.push_back(Grid::FromHandle(d_in.grids[i]));
     if (multi && g0) {
       // the 3-D grid of the sweep that is decomposed decides the cut
       const Grid *cut = nullptr;
       for (int i = 0; i < d_in.num_grids && !cut; ++i)
         if (Grid::FromHandle(d_in.grids[i])->decomposed) cut = Grid::FromHandle(d_in.grids[i]);
       if (cut) p->empty = !LocaliseDomain(cut, &p->dom, false);
+      // a generated kernel reads its z neighbours from the halo planes: they must be as wide
+      // as its reach (the reference derives the halo width from the same number,
+      // runtime/grid_space_mpi.h:42-62,337-340; here it is the option `halo`)
+      for (int i = 0; i < d_in.num_grids; ++i) {
+        const Grid *g = Grid::FromHandle(d_in.grids[i]);
+        if (!g->decomposed) continue;
+        if (std::max(d_in.z_reach, 1) > g->halo) {
+          fprintf(stderr, "[physis-b200] sweep '%s' reads %d planes beyond its own in z but grid %d has "
+                          "%d halo plane(s) per side: run with PHYSIS_B200_OPTIONS=halo=%d (or on one GPU)\n",
+                  p->name.c_str(), d_in.z_reach, g->id, g->halo, d_in.z_reach);
+          exit(1);
+        }
+      }
       // which grids a generated kernel writes is only known to the translator
       // (written_mask); without it every grid of the sweep is refreshed
       for (int i = 0; i < d_in.num_grids; ++i) {
@@ -191,6 +232,18 @@ void LaunchSweep(Runtime *rt, SweepPlan *p) {
   // rank are complete, and they no longer read the halo planes this sweep overwrites
   const bool self_sync = multi && p->fused_sync && !p->empty;
   if (multi && !self_sync) rt->WaitNeighbours(rt->sweep_epoch);
+  // what the grids hold after this sweep
+  const bool keep_sum = p->sum_grid && (p->himeno || p->empty) && p->sum_grid->ZeroOutside(p->gdom);
+  for (Grid *g : p->outputs) g->NoteEmit(p->gdom);
+  if (p->sum_grid) {
+    p->sum_grid->NoteEmit(p->gdom);
+    if (keep_sum) {
+      // everything outside the domain is still the zero fill: the per-CTA partials of this launch
+      // add up to the sum of the whole grid (a rank without a share of the domain contributes 0)
+      p->sum_grid->sum_cache.valid = true;
+      p->sum_grid->sum_cache.count = p->empty ? 0 : HimenoPartialCount(p->himeno);
+    }
+  }
   if (!p->empty) {
     if (p->star7) LaunchStar7(rt, p->star7);
     else if (p->himeno) LaunchHimeno(rt, p->himeno);
@@ -268,6 +321,7 @@ extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200St
         ++rt->sweep_epoch;
         rt->SignalNeighbours(rt->sweep_epoch);
       }
+      for (int s = 0; s < 2; ++s) Grid::FromHandle(descs[0].grids[s])->NoteEmit(descs[0].dom);
       for (int i = 0; i < first_unfused; ++i) {
         LaunchStar7Pair(rt, pair, i & 1);
         if (multi) ++rt->sweep_epoch;

@@ -58,18 +58,46 @@ struct SlabSync {
   unsigned *done;          // CTAs of this launch that have finished (self-resetting)
   uint32_t wait_epoch;     // neighbours must have completed this many sweeps
   uint32_t signal_epoch;   // the number this sweep publishes
+  // a neighbour that stays silent longer than this is reported through `err` (host-mapped
+  // words read by Runtime::CheckDeviceErrors) instead of hanging or killing the context
+  unsigned long long timeout_ns;
+  uint32_t *err;
   // Overlap of the exchange with interior compute: work items are ordered so that the z chunks
-  // touching the slab's two ends come first (SlabChunkOrder); once these `boundary_items`
-  // items are done -- the halo planes the neighbours wait for are delivered and this rank's own
-  // halo planes are no longer read -- the sweep publishes its number, and the rest of the sweep
-  // (the interior chunks) runs while the signal travels.  0: publish when the whole sweep is done.
+  // touching the slab's two ends come first (SlabChunkOrder): the first `nb_lo` and the last
+  // `nb_hi` chunks -- every chunk that reads a halo plane or computes a plane the neighbours
+  // receive.  Once these `boundary_items` items are done -- the halo planes the neighbours wait
+  // for are delivered and this rank's own halo planes are no longer read -- the sweep publishes
+  // its number, and the rest of the sweep (the interior chunks) runs while the signal travels.
+  // 0: publish when the whole sweep is done.
   int boundary_items;
+  int nb_lo, nb_hi;
 };
 
-// z chunk a work item with chunk sequence number `seq` processes: 0, nzc-1, 1, 2, ..., nzc-2
-__device__ __forceinline__ int SlabChunkOrder(const SlabSync &s, int seq, int nzc) {
-  if (s.boundary_items == 0 || nzc < 3) return seq;
-  return seq == 0 ? 0 : (seq == 1 ? nzc - 1 : seq - 1);
+// Host side: which chunks are boundary chunks.  `reach` = planes a sweep reads beyond / delivers
+// from each end of the slab (1 for a single sweep, 2 for the fused two-sweep pass); chunks are
+// `zc` planes long, the last one `nz - (nzc-1)*zc`.
+inline void SlabSyncSetBoundary(SlabSync *s, bool early, int nz, int zc, int nzc, int tiles, int reach) {
+  s->boundary_items = 0;
+  s->nb_lo = s->nb_hi = 0;
+  if (!early || !s->done) return;
+  const int last = nz - (nzc - 1) * zc;
+  int lo = (reach + zc - 1) / zc;                       // chunks covering the first `reach` planes
+  int hi = 1 + (reach > last ? (reach - last + zc - 1) / zc : 0);  // ... and the last `reach`
+  if (lo + hi >= nzc) {          // every chunk is a boundary chunk: natural order
+    s->boundary_items = nzc * tiles;
+    return;
+  }
+  s->nb_lo = lo;
+  s->nb_hi = hi;
+  s->boundary_items = (lo + hi) * tiles;
+}
+
+// z chunk a work item with chunk sequence number `seq` processes: the nb_lo lowest chunks, the
+// nb_hi highest, then the interior ones in order
+__host__ __device__ __forceinline__ int SlabChunkOrder(const SlabSync &s, int seq, int nzc) {
+  const int nb = s.nb_lo + s.nb_hi;
+  if (nb == 0) return seq;
+  return seq < s.nb_lo ? seq : (seq < nb ? nzc - nb + seq : seq - s.nb_hi);
 }
 
 __device__ __forceinline__ uint32_t LdAcquireSys(const uint32_t *p) {
@@ -81,16 +109,48 @@ __device__ __forceinline__ void StReleaseSys(uint32_t *p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long GlobalTimerNs() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Spins until both flag words have reached `epoch`.  A lost signal becomes an error the host
+// reports (which neighbour, which sweep, what was seen), not a hang and not a dead context:
+// the bound is wall time (option sync_timeout_s), so profiler serialisation or ranks
+// time-slicing one GPU do not trip it.  Out of line: the spin loop must not take part in the
+// sweeps' register allocation.
+static __device__ __noinline__ void SlabWaitFlags(const uint32_t *flags, uint32_t epoch,
+                                                  unsigned long long timeout_ns, uint32_t *err) {
+  for (int i = 0; i < 2; ++i) {
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
+    uint32_t seen;
+    while ((int32_t)((seen = LdAcquireSys(flags + i)) - epoch) < 0) {
+      __nanosleep(64);
+      if ((++spins & 4095u) == 0) {
+        const unsigned long long now = GlobalTimerNs();
+        if (t0 == 0) t0 = now;
+        volatile uint32_t *e = err;
+        if (e && e[0] != 0) return;  // another CTA has already given up
+        if (now - t0 > timeout_ns) {
+          if (e) {
+            e[1] = epoch; e[2] = seen; e[3] = blockIdx.x;
+            __threadfence_system();
+            e[0] = 1u + (uint32_t)i;
+            __threadfence_system();
+          }
+          return;
+        }
+      }
+    }
+  }
+}
+
 // Called by thread 0 of every CTA before the CTA's first __syncthreads().
 __device__ __forceinline__ void SlabSyncWait(const SlabSync &s) {
   if (!s.flags) return;
-  for (int i = 0; i < 2; ++i) {
-    uint32_t spins = 0;
-    while ((int32_t)(LdAcquireSys(s.flags + i) - s.wait_epoch) < 0) {
-      __nanosleep(64);
-      if (++spins > (1u << 26)) __trap();  // a lost signal becomes an error, not a hang
-    }
-  }
+  SlabWaitFlags(s.flags, s.wait_epoch, s.timeout_ns, s.err);
 }
 
 // Called by every consumer thread of a CTA after it has finished work item `item`: the last

@@ -83,6 +83,43 @@ def case_pair():
         api.PSFinalize()
 
 
+def case_pair_tail():
+    """Early signal with a one-plane tail chunk (nz_loc % zc == 1) and more work items than CTA
+    slots: the boundary items must include the second-last chunk (star7_pair.cu, sweep_common.cuh
+    SlabSyncSetBoundary).  Repeated, since a race shows only sometimes."""
+    from physis_b200 import api
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    co64 = np.array([0.1234567] * 6 + [0.2592598])
+    for shape, iters, opts, reps in [((512, 512, 21 * world), 4, ("star7_pair_zc=5",), 12),
+                                     ((256, 64, 9 * world), 5, ("star7_pair_zc=1",), 6),
+                                     ((128, 40, 13 * world), 5, ("star7_pair_zc=4",), 6)]:
+        nx, ny, nz = shape
+        api.PSInit(["t"], 3, shape)
+        for kv in opts:
+            api.set_option(kv)
+        a, b = api.Grid(shape, api.PS_FLOAT), api.Grid(shape, api.PS_FLOAT)
+        rng = np.random.default_rng(nx + nz)
+        f0 = rng.random(nx * ny * nz, dtype=np.float32)
+        g0 = rng.random(nx * ny * nz, dtype=np.float32)
+        dom = api.PSDomain3DNew(0, nx, 0, ny, 0, nz)
+        co = [float(np.float32(c)) for c in co64]
+        d0 = api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, dom, [a, b], co)
+        d1 = api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, dom, [b, a], co)
+        want_a = H.diffusion7_numpy(f0, shape, co64.astype(np.float32), 2 * iters)
+        want_b = H.diffusion7_numpy(f0, shape, co64.astype(np.float32), 2 * iters - 1)
+        for rep in range(reps):
+            a.copyin(f0)
+            b.copyin(g0)
+            api.rt().__PSB200ResetStats()
+            api.stencil_run(iters, [d0, d1])
+            assert int(api.stats().fused_pairs) == ((iters - 1) & ~1), shape
+            check(f"tail A {shape} rep {rep}", want_a, a.copyout(), np.uint32)
+            check(f"tail B {shape} rep {rep}", want_b, b.copyout(), np.uint32)
+        a.free()
+        b.free()
+        api.PSFinalize()
+
+
 def case_himeno():
     for dims, nn in [((64, 32, 32), 4), ((128, 20, 13), 2)]:
         a = H.run_himeno(H.oracle_port(), dims, nn, gosa=True, seed=5)
@@ -140,9 +177,8 @@ def case_api():
 
 
 def case_golden():
-    """The reference's system tests through the generic path on z-slabs (halo=2 for the
-    asymmetric stencil).  Not covered here: generated kernels that wrap periodically in z and
-    array members of user types (single-GPU features this round)."""
+    """A subset of the reference's system tests through the generic path on z-slabs (halo=2 for
+    the asymmetric stencil); case_golden_all runs every one."""
     import test_golden_suite as G
     names = ["test_7-pt", "test_7-pt-multi-iterations", "test_7-pt-double-type", "test_7-pt-int-type",
              "test_16", "test_15", "test_27-pt", "test_asymmetric", "test_stencil-hole",
@@ -158,7 +194,19 @@ def case_golden():
         assert G.sha(G.stdout_of(n, got)) == G.GOLD[n]["sha256"], n
 
 
-CASES = {"golden": case_golden, "diffusion": case_diffusion, "pair": case_pair, "himeno": case_himeno, "pstag": case_pstag, "api": case_api}
+def case_golden_all():
+    """All 36 reference system tests with a twin on z-slabs: also the kernels that wrap
+    periodically in z (the wrap is the ring exchange: rank 0's lower halo holds the last plane)
+    and user types with array members (component stride = the rank's allocation)."""
+    import test_golden_suite as G
+    for n in sorted(G.SUITE):
+        want = G.run_golden(H.oracle_port(), n)
+        got = G.run_golden(H.b200_programs(), n)
+        assert got.tobytes() == want.tobytes(), n
+        assert G.sha(G.stdout_of(n, got)) == G.GOLD[n]["sha256"], n
+
+
+CASES = {"golden": case_golden, "golden_all": case_golden_all, "pair_tail": case_pair_tail, "diffusion": case_diffusion, "pair": case_pair, "himeno": case_himeno, "pstag": case_pstag, "api": case_api}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

@@ -1,6 +1,13 @@
-"""GPU, N >= 2: z-slab decomposition + NVLink halo exchange, one process per GPU (SPMD).
-Every rank compares the full result of each program with the CPU oracle, for the fused
-(in-kernel peer store) and the copy-based halo exchange and both flag mechanisms."""
+"""GPU, N >= 2 ranks: z-slab decomposition + halo exchange through CUDA-IPC peer mappings, one
+process per rank (SPMD).  Every rank compares the full result of each program with the CPU
+oracle, for the fused (in-kernel peer store) and the copy-based halo exchange and both flag
+mechanisms.
+
+Ranks map to GPUs round-robin (LOCAL_RANK % device count, as PSInit does): on a box with at
+least N GPUs every rank has its own and the exchange crosses NVLink; on a box with fewer the
+ranks time-slice a GPU and the same code path -- IPC mappings, in-kernel flags, peer stores --
+runs through device-local memory.  The protocol logic is checked either way; only the
+physical link differs."""
 import os
 import socket
 import subprocess
@@ -32,8 +39,9 @@ def _free_port():
 def _run(world, cases, options=""):
     port = _free_port()
     procs = []
+    ngpus = max(_ngpus(), 1)
     for r in range(world):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r),
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r % ngpus),
                    MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PHYSIS_B200_OPTIONS=options)
         procs.append(subprocess.Popen([sys.executable, os.path.join(H.ROOT, "tests", "mgpu_worker.py")] + cases,
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
@@ -49,31 +57,43 @@ def _run(world, cases, options=""):
         assert p.returncode == 0, f"rank {r} of {world} ({options}):\n{o[-3000:]}"
 
 
-@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
 @pytest.mark.parametrize("options", ["halo_push=1", "halo_push=0", "halo_push=1,sync_mode=1",
                                      "halo_push=1,sync_mode=0", "halo_push=0,sync_mode=0"])
 def test_two_gpus_match_oracle(options):
     _run(2, ["diffusion", "pair", "himeno", "pstag", "api"], options)
 
 
-@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
 def test_two_gpus_reference_system_tests():
     _run(2, ["golden"], "halo=2")
 
 
-@pytest.mark.skipif(_ngpus() < 4, reason="needs at least 4 GPUs")
 def test_four_gpus_match_oracle():
     _run(4, ["diffusion", "pair", "himeno", "pstag", "api"], "halo_push=1")
 
 
-@pytest.mark.skipif(_ngpus() < 3, reason="needs at least 3 GPUs")
 def test_three_gpus_uneven_slabs():
     _run(3, ["diffusion", "pair", "pstag", "api"], "halo_push=0")
 
 
-@pytest.mark.skipif(_ngpus() < 3, reason="needs at least 3 GPUs")
 def test_three_gpus_fused_pairs_uneven_slabs():
     _run(3, ["pair", "diffusion"], "halo_push=1")
+
+
+def test_two_ranks_early_signal_with_one_plane_tail_chunk():
+    # regression for the early-signal window: slabs of 21 planes in chunks of 5 leave a
+    # one-plane tail chunk, so the second-last chunk also delivers / reads halo planes; more
+    # work items than CTA slots, repeated runs, bits against the oracle every time
+    _run(2, ["pair_tail"], "halo_push=1")
+
+
+def test_eight_ranks_match_oracle():
+    _run(8, ["diffusion", "pair", "himeno", "pstag", "api"], "halo_push=1")
+
+
+def test_two_ranks_full_reference_system_test_suite():
+    # every reference system test with an expected-output twin, incl. kernels that wrap
+    # periodically in z across the rank ring and user types with array members
+    _run(2, ["golden_all"], "halo=2")
 
 
 def test_single_process_group_of_one():
