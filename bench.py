@@ -308,24 +308,40 @@ def himeno_line(args, api, lib, world, dist):
     out = {}
     pts = (mi - 2) * (mj - 2) * (gmk - 2)
     peak, _ = _peaks()
+    lib.himeno_jacobi_gosa_each.argtypes = [C.c_int]
+    lib.himeno_jacobi_gosa_each.restype = C.c_float
     for with_gosa in (0, 1):
+        # with_residual: the original benchmark's structure -- the residual of every iteration:
+        # each PSStencilRun of the ping-pong pair (two sweeps, ss*ss emitted) is followed by
+        # PSReduce(&gosa, PS_SUM, gosa_g), which folds the per-CTA partial sums the sweep left
+        run = (lambda: lib.himeno_jacobi_gosa_each(nn)) if with_gosa else (lambda: lib.himeno_sweeps_only(nn, 0))
         for _ in range(2):
-            lib.himeno_sweeps_only(nn, with_gosa)
+            run()
         api.rt().__PSB200Synchronize()
         _barrier(dist)
+        api.rt().__PSB200ResetStats()
         api.rt().__PSB200TimerStart()
-        lib.himeno_sweeps_only(nn, with_gosa)
-        gosa = lib.himeno_reduce_gosa() if with_gosa else 0.0
+        gosa = run()
         ms = api.rt().__PSB200TimerStopMs()
         _barrier(dist)
         ms = _max_over_ranks(dist, ms)
-        bpl = 64 if with_gosa else 56
+        # 12 coefficient/source reads + p read + p write (himenobmtxpa_physis.c:418-432), + the
+        # 4-byte ss*ss emit; the reduction reads one fp64 per CTA, not the grid
+        bpl = 60 if with_gosa else 56
         key = "with_residual" if with_gosa else "sweep_only"
         gbs = pts * nn * bpl / ms / 1e6
         out[key] = {"glups": pts * nn / ms / 1e6, "ms_per_sweep": ms / nn,
                     "alg_bytes_per_lup": bpl, "gbs": gbs, "roofline_frac_per_gpu": gbs / world / peak}
         if with_gosa:
-            out[key]["gosa"] = float(gosa)
+            st = api.stats()
+            # the same sum by a full pass over the emitted grid (GPU, fp32 tree)
+            api.set_option("reduce_fuse=0")
+            full = float(lib.himeno_reduce_gosa())
+            api.set_option("reduce_fuse=1")
+            out[key].update({"gosa": float(gosa), "gosa_full_pass": full,
+                             "gosa_ok": bool(abs(float(gosa) - full) <= 2e-5 * abs(full)),
+                             "reduces": nn // 2, "reduces_from_partials": int(st.reduces_from_partials),
+                             "schedule": "PSStencilRun(pair, 1) + PSReduce per iteration"})
     lib.himeno_finalize()
     out["size"] = f"{mi}x{mj}x{gmk} over {world} GPU(s)"
     out["sweeps"] = nn
@@ -408,6 +424,128 @@ def pstag_line(args, api, lib, world, dist):
             "size": f"{n}x{n}x{gnz} cells over {world} GPU(s)", "sweeps": count, "dtype": "f64"}
 
 
+def expected_samples(n, gnz, z_off, idx, sweeps, co):
+    """Exact solution of the DISCRETE problem at flat slab indices `idx` after `sweeps` sweeps:
+    the benchmark's initial field 0.125 * prod_d (1 - cos(theta_d)) is a sum of cell-centred cosine
+    modes, each an eigenvector of the clamped 7-point update, so the field after T sweeps is
+    0.125 * sum over subsets S of axes of (-1)^|S| * lambda_S^T * prod_{d in S} cos(theta_d),
+    lambda_S = cc + sum_d (c_d- + c_d+) * (cos(2 pi / n_d) if d in S else 1).  fp64; independent of
+    the oracle."""
+    ce, cw, cn, cs, ct, cb, cc = [float(np.float32(c)) for c in co]
+    i = idx % n
+    j = (idx // n) % n
+    k = idx // (n * n) + z_off
+    th = [2 * np.pi * (i + 0.5) / n, 2 * np.pi * (j + 0.5) / n, 2 * np.pi * (k + 0.5) / gnz]
+    pair = [ce + cw, cn + cs, ct + cb]
+    step = [np.cos(2 * np.pi / n), np.cos(2 * np.pi / n), np.cos(2 * np.pi / gnz)]
+    out = np.zeros(idx.size, np.float64)
+    for mask in range(8):
+        lam, term, sign = cc, np.ones(idx.size, np.float64), 1.0
+        for d in range(3):
+            if mask >> d & 1:
+                lam += pair[d] * step[d]
+                term = term * np.cos(th[d])
+                sign = -sign
+            else:
+                lam += pair[d]
+        out += sign * (lam ** sweeps) * term
+    return 0.125 * out
+
+
+def parity_check(world, rank, dist):
+    """After the timed regions: one small fixed case per kernel family, run across the ranks
+    through the same C ABI and compared bit for bit with the CPU oracle (the checker, never the
+    thing measured).  Returns (ok on every rank, sha256 of rank 0's GPU results, case names)."""
+    import hashlib
+    import helpers as H
+    port, prog = H.oracle_port(), H.b200_programs()
+    h = hashlib.sha256()
+    ok, cases = True, []
+
+    def same(name, want, got):
+        nonlocal ok
+        w, g = np.ascontiguousarray(want), np.ascontiguousarray(got)
+        good = w.tobytes() == g.tobytes()
+        ok = ok and good
+        cases.append(name if good else name + " MISMATCH")
+        h.update(g.tobytes())
+
+    rng = np.random.default_rng(1234)
+    iso = np.array([0.1] * 6 + [0.4], np.float32)
+    gen = np.array([0.11, 0.07, 0.13, 0.05, 0.17, 0.03, 0.44], np.float32)
+    for (nx, ny, nz), count, co in [((256, 48, 8 * world), 6, iso), ((512, 20, 8 * world), 8, gen),
+                                    ((1024, 24, 8 * world), 6, iso)]:
+        f0 = rng.random(nx * ny * nz, dtype=np.float32)
+        same(f"diffusion7 {nx}x{ny}x{nz} x{count}", H.run_diffusion(port, f0, nx, ny, nz, count, co),
+             H.run_diffusion(prog, f0, nx, ny, nz, count, co))
+    dims = (128, 24, 4 * world + 2)
+    a = H.run_himeno(port, dims, 4, gosa=True, seed=5, each=True)
+    b = H.run_himeno(prog, dims, 4, gosa=True, seed=5, each=True)
+    same(f"himeno19 {dims} p0", a[0], b[0])
+    same(f"himeno19 {dims} p1", a[1], b[1])
+    same(f"himeno19 {dims} ss^2", a[3], b[3])
+    exact = float(np.sum(a[3].astype(np.float64)))
+    good = abs(b[2] - exact) <= 8e-6 * abs(exact)
+    ok = ok and good
+    cases.append("himeno19 gosa vs fp64 sum" + ("" if good else " MISMATCH"))
+    nx, ny, nz = 128, 32, 4 * world
+    u, kap = H.pstag_inputs(nx, ny, nz)
+    same(f"periodic7_staggered {nx}x{ny}x{nz} x3", H.run_pstag(port, u, kap, nx, ny, nz, 3),
+         H.run_pstag(prog, u, kap, nx, ny, nz, 3))
+    if dist is not None:
+        import torch
+        t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item() > 0.5)
+    return ok, h.hexdigest(), cases
+
+
+def small_runs_line(args, api, lib, world, dist):
+    """Extra: BASELINE config 1's grid (256^3 per GPU, 100 sweeps) on the GPU -- through one
+    PSStencilRun(50 iterations) and through the common idiom of 50 PSStencilRun(1 iteration)
+    calls (no fused passes: one run call covers two sweeps; prepared plans are reused)."""
+    n, sweeps = 256, 100
+    gnz = n * world
+    co = [0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.4]
+    lib.initialize_physis(0, None, n, n, gnz)
+    lib.initialize_benchmark_physis(n, n, gnz)
+    zo, zl = C.c_int(), C.c_int()
+    lib.local_size_physis(C.byref(zo), C.byref(zl))
+    i = np.arange(n, dtype=np.float64)
+    ax = (1.0 - np.cos(2 * np.pi * (i + 0.5) / n)).astype(np.float32)
+    k = np.arange(zo.value, zo.value + zl.value, dtype=np.float64)
+    az = (1.0 - np.cos(2 * np.pi * (k + 0.5) / gnz)).astype(np.float32)
+    f0 = (0.125 * az[:, None, None] * ax[None, :, None] * ax[None, None, :]).astype(np.float32).ravel()
+    lib.copyin_local_physis(f0.ctypes.data)
+    lib.run_sweeps_iter1_physis.argtypes = [C.c_int] * 4 + [C.c_float] * 7
+    r = api.rt()
+    out = {}
+    for key, fn in (("one_run_call", lib.run_sweeps_only_physis), ("iter1_loop", lib.run_sweeps_iter1_physis)):
+        for _ in range(3):
+            fn(sweeps, n, n, gnz, *co)
+        r.__PSB200Synchronize()
+        _barrier(dist)
+        r.__PSB200ResetStats()
+        t0 = time.perf_counter()
+        r.__PSB200TimerStart()
+        reps = 5
+        for _ in range(reps):
+            fn(sweeps, n, n, gnz, *co)
+        host_ms = (time.perf_counter() - t0) * 1e3   # time to ENQUEUE (the host never synchronises)
+        ms = r.__PSB200TimerStopMs()
+        _barrier(dist)
+        ms = _max_over_ranks(dist, ms)
+        st = api.stats()
+        out[key] = {"glups": n * n * gnz * sweeps * reps / ms / 1e6, "ms_per_sweep": ms / (sweeps * reps),
+                    "host_enqueue_ms_per_sweep": host_ms / (sweeps * reps),
+                    "launches_per_100_sweeps": int(st.kernel_launches) // reps,
+                    "plan_cache_hits": int(st.plan_cache_hits)}
+    lib.finalize_benchmark_physis()
+    out["size"] = f"{n}x{n}x{gnz} over {world} GPU(s), {sweeps} sweeps (BASELINE config 1's grid per GPU)"
+    out["l2"] = "working set 134 MB per GPU ~ L2 (126 MB): partly L2-resident, not an HBM roofline case"
+    return out
+
+
 def run_b200(args, rank, world, dist):
     import physis_b200
     from physis_b200 import api
@@ -485,6 +623,12 @@ def run_b200(args, rank, world, dist):
     ms_e2e = _max_over_ranks(dist, ms_e2e)
     e2e = npts_glob * count * args.steps / ms_e2e / 1e6
     checksum = float(np.sum(host[::4097], dtype=np.float64))
+    # ... against the exact solution of the discrete problem after count*steps sweeps (fp64)
+    idx = np.arange(0, npts_loc, 4097, dtype=np.int64)
+    want_sum = float(np.sum(expected_samples(n, gnz, z_off, idx, count * args.steps, co)))
+    checksum_ok = abs(checksum - want_sum) <= 2e-4 * abs(want_sum)
+    if dist is not None:
+        checksum_ok = _max_over_ranks(dist, 0.0 if checksum_ok else 1.0) == 0.0
 
     # ---- roofline of the dominant kernel (per GPU) ------------------------------
     peak, peak_src = _peaks()
@@ -533,7 +677,7 @@ def run_b200(args, rank, world, dist):
                    "options": args.opt, "cpu_binding": args.cpu_binding},
         "e2e": {"value": e2e, "unit": "GLUP/s", "h2d_bytes_per_step": npts_loc * 4 * world,
                 "d2h_bytes_per_step": npts_loc * 4 * world, "ms_per_step": ms_e2e / args.steps,
-                "checksum": checksum},
+                "checksum": checksum, "checksum_expected": want_sum, "checksum_ok": bool(checksum_ok)},
         "gpu_launches": launches,
         "roofline": roofline,
         "clocks": clocks,
@@ -547,6 +691,15 @@ def run_b200(args, rank, world, dist):
         line["periodic_staggered_fp64"] = ps
     if not args.no_strong and not args.strong and 1024 % world == 0:
         line["strong_scaling_1024"] = strong_line(args, api, lib, world, dist)
+    if not args.no_small:
+        line["config1_256"] = small_runs_line(args, api, lib, world, dist)
+    if not args.no_parity:
+        ok, sha, cases = parity_check(world, rank, dist)
+        line["parity_ok"] = bool(ok and checksum_ok and
+                                 line.get("himeno", {}).get("with_residual", {}).get("gosa_ok", True))
+        line["parity"] = {"oracle": "oracle/liboracle.so (CPU restatement of the REFERENCE target)",
+                          "bit_exact_cases": cases, "sha256_of_gpu_results": sha,
+                          "checksum_vs_exact_discrete_solution": bool(checksum_ok), "ranks": world}
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample()
     if rank == 0:
@@ -564,6 +717,8 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="runtime option key=value")
     ap.add_argument("--no-himeno", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run parity cases against the oracle")
+    ap.add_argument("--no-small", action="store_true", help="skip the 256^3 / iter=1-loop entry")
     ap.add_argument("--himeno", default="XL")
     ap.add_argument("--himeno-nn", type=int, default=20)
     ap.add_argument("--pstag-size", type=int, default=512)

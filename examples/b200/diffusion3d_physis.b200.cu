@@ -162,6 +162,18 @@ void run_sweeps_only_physis(int count, int nx, int ny, int nz,
                    __PSStencilMap_kernel_physis(dom, f2g, f1g,
                                                 ce, cw, cn, cs, ct, cb, cc));
 }
+/* the common Physis idiom `for (i < n) PSStencilRun(..., 1);` (one run call per iteration) */
+void run_sweeps_iter1_physis(int count, int nx, int ny, int nz,
+                             REAL ce, REAL cw, REAL cn, REAL cs,
+                             REAL ct, REAL cb, REAL cc) {
+  PSDomain3D dom = PSDomain3DNew(0, nx, 0, ny, 0, nz);
+  for (int i = 0; i < count / 2; ++i)
+    __PSStencilRun_0(1,
+                     __PSStencilMap_kernel_physis(dom, f1g, f2g,
+                                                  ce, cw, cn, cs, ct, cb, cc),
+                     __PSStencilMap_kernel_physis(dom, f2g, f1g,
+                                                  ce, cw, cn, cs, ct, cb, cc));
+}
 void copyin_physis(const REAL *f1_host) { __PSGridCopyin(f1g, f1_host, NULL); }
 /* multi-GPU bench hooks: this rank's slab only (see __PSB200GridCopyinLocal) */
 void copyin_local_physis(const REAL *slab) { __PSB200GridCopyinLocal(f1g, slab); }

@@ -106,6 +106,26 @@ template <typename S> struct ZReachOf { static constexpr int v = 0; };
   }                                                                                             \
   B200_DESCRIBE(K, 2, s->g1, s->g2)
 #define DEF_STENCIL_2(K, ND) DEF_STENCIL_2X(K, 1)
+/* two grids and a float scalar (passed to the __global__ by value, as the CUDA target does,
+ * translator/cuda_runtime_builder.cc:1615-1641) */
+#define DEF_STENCIL_2F(K)                                                                       \
+  struct __PSStencil_##K { PSDomain3D dom; __PSGrid *g1; int g1_index; __PSGrid *g2; int g2_index; float c; }; \
+  static struct __PSStencil_##K __PSStencilMap_##K(PSDomain3D dom, __PSGrid *g1, __PSGrid *g2, float c) { \
+    struct __PSStencil_##K stencil = {dom, g1, __PSGridGetID(g1), g2, __PSGridGetID(g2), c};    \
+    return stencil;                                                                             \
+  }                                                                                             \
+  __global__ void __PSStencilRun_##K(__PSDomain dom, int zchunk, GV3 g1, GV3 g2, float c) {     \
+    __PSB200_FOREACH_POINT_BEGIN(dom, zchunk, x, y, z)                                          \
+      K(x, y, z, &g1, &g2, c);                                                                  \
+    __PSB200_FOREACH_POINT_END                                                                  \
+  }                                                                                             \
+  static void __PSStencilLaunch_##K(const void *sv, const __PSDomain *dom, __PSB200Stream st) { \
+    const struct __PSStencil_##K *s = (const struct __PSStencil_##K *)sv;                       \
+    __PSB200GenericShape sh = __PSB200GenericShapeFor(dom, 3);                                  \
+    __PSStencilRun_##K<<<sh.grid, sh.block, 0, (cudaStream_t)st>>>(                             \
+        *dom, sh.zchunk, MakeGV3(s->g1, 1), MakeGV3(s->g2, 1), s->c);                           \
+  }                                                                                             \
+  B200_DESCRIBE(K, 2, s->g1, s->g2)
 #define DEF_STENCIL_2U(K, NM) DEF_STENCIL_2X(K, NM)
 
 #define DEF_STENCIL_3G(K, T3, MAKE3)                                                            \

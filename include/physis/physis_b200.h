@@ -337,6 +337,15 @@ typedef struct {
   double fused_pair_ms;       /* ... and their accumulated device time (CUDA events) */
   uint64_t reduces_from_partials; /* PSReduce calls answered from the partial sums the producing
                                    * sweep left behind instead of a pass over the grid */
+  uint64_t plan_cache_hits;       /* sweeps whose prepared plan (TMA descriptors, launch shape) was
+                                   * reused from an earlier __PSB200StencilRun */
+  /* halo-exchange profile of multi-GPU sweeps (option halo_profile=1; cf. the reference's
+   * per-grid DataCopyProfile, runtime/timing.h:11-18, grid_space_mpi_cuda.h:556-569): time the
+   * sweeps' CTAs spent waiting for the ring neighbours before touching halo planes */
+  uint64_t halo_wait_ns_sum;      /* summed over the CTAs that waited */
+  uint64_t halo_wait_ns_max;      /* longest single wait */
+  uint64_t halo_wait_ctas;        /* CTAs that waited (boundary work items only) */
+  uint64_t halo_wait_launches;    /* sweeps that took part */
 } __PSB200Stats;
 void __PSB200GetStats(__PSB200Stats *out);
 void __PSB200ResetStats(void);

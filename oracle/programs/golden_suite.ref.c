@@ -57,6 +57,16 @@
     REF_LOOP(K(i1, i2, i3, s->g1, s->g2))                                              \
   }
 #define DEF_STENCIL_2U(K, NM) DEF_STENCIL_2(K, 3)
+/* two grids and a float scalar: scalars are copied into the stencil struct after the grids */
+#define DEF_STENCIL_2F(K)                                                              \
+  struct __PSStencil_##K { PSDomain3D dom; __PSGrid *g1; int g1_index; __PSGrid *g2; int g2_index; float c; }; \
+  static struct __PSStencil_##K __PSStencilMap_##K(PSDomain3D dom, __PSGrid *g1, __PSGrid *g2, float c) { \
+    struct __PSStencil_##K stencil = {dom, g1, __PSGridGetID(g1), g2, __PSGridGetID(g2), c}; \
+    return stencil;                                                                    \
+  }                                                                                    \
+  static void __PSStencilRun_##K(const struct __PSStencil_##K *const s) {              \
+    REF_LOOP(K(i1, i2, i3, s->g1, s->g2, s->c))                                        \
+  }
 #define DEF_STENCIL_3(K, ND)                                                           \
   struct __PSStencil_##K { PSDomain3D dom; __PSGrid *g1; int g1_index; __PSGrid *g2; int g2_index; \
                            __PSGrid *g3; int g3_index; };                              \

@@ -54,7 +54,9 @@ class Stats(C.Structure):
                 ("d2h_bytes", C.c_uint64), ("halo_bytes", C.c_uint64),
                 ("last_kernel_ms", C.c_float), ("fused_pairs", C.c_uint64),
                 ("fused_pairs_timed", C.c_uint64), ("fused_pair_ms", C.c_double),
-                ("reduces_from_partials", C.c_uint64)]
+                ("reduces_from_partials", C.c_uint64), ("plan_cache_hits", C.c_uint64),
+                ("halo_wait_ns_sum", C.c_uint64), ("halo_wait_ns_max", C.c_uint64),
+                ("halo_wait_ctas", C.c_uint64), ("halo_wait_launches", C.c_uint64)]
 
 
 # every extern "C" symbol include/physis/physis_b200.h declares

@@ -25,6 +25,7 @@
 #include "runtime.h"
 #include "tma.cuh"
 #include "sweep_common.cuh"
+#include "himeno_math.cuh"
 
 #include <algorithm>
 #include <string>
@@ -58,29 +59,6 @@ struct HimenoArgs {
 
 __device__ __forceinline__ float4 LdStream(const float *p) {
   return __ldcs(reinterpret_cast<const float4 *>(p));
-}
-
-// One output point.  pXYZ naming: m = -1, c = 0, p = +1 for (x, y, z).
-__device__ __forceinline__ float Jacobi(float a0, float a1, float a2, float a3, float b0,
-                                        float b1, float b2, float c0, float c1, float c2,
-                                        float bnd, float wrk1, float omega,
-                                        float ccc, float ccp, float cpc, float pcc, float cpp,
-                                        float cmp, float cpm, float cmm, float ppc, float pmc,
-                                        float mpc, float mmc, float pcp, float pcm, float mcp,
-                                        float mcm, float ccm, float cmc, float mcc, float *ss_out) {
-  float s0 = MulRn(a0, ccp);
-  s0 = AddRn(s0, MulRn(a1, cpc));
-  s0 = AddRn(s0, MulRn(a2, pcc));
-  s0 = AddRn(s0, MulRn(b0, AddRn(SubRn(SubRn(cpp, cmp), cpm), cmm)));
-  s0 = AddRn(s0, MulRn(b1, AddRn(SubRn(SubRn(ppc, pmc), mpc), mmc)));
-  s0 = AddRn(s0, MulRn(b2, AddRn(SubRn(SubRn(pcp, pcm), mcp), mcm)));
-  s0 = AddRn(s0, MulRn(c0, ccm));
-  s0 = AddRn(s0, MulRn(c1, cmc));
-  s0 = AddRn(s0, MulRn(c2, mcc));
-  s0 = AddRn(s0, wrk1);
-  const float ss = MulRn(SubRn(MulRn(s0, a3), ccc), bnd);
-  *ss_out = ss;
-  return AddRn(ccc, MulRn(omega, ss));
 }
 
 // TY rows per CTA tile, one row per consumer warp, one box (128 floats) wide.
@@ -237,7 +215,7 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
           const float t_xm = (j == 0) ? t_w : Elem(t_c, j - 1);
           const float t_xp = (j == VEC - 1) ? t_e : Elem(t_c, j + 1);
           float ss;
-          const float v = Jacobi(
+          const float v = HimenoJacobi(
               Elem(va0, j), Elem(va1, j), Elem(va2, j), Elem(va3, j), Elem(vb0, j), Elem(vb1, j),
               Elem(vb2, j), Elem(vc0, j), Elem(vc1, j), Elem(vc2, j), Elem(vbnd, j), Elem(vwrk, j),
               a.omega,

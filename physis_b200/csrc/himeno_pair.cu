@@ -1,0 +1,495 @@
+// Two Himeno 19-point Jacobi sweeps in one pass over HBM (temporal blocking).
+//
+// PSStencilRun(map(jacobi, p0 -> p1), map(jacobi, p1 -> p0), nn/2) -- the shape of
+// examples/himeno/himenobmtxpa_physis.c:364-393 -- applies the same update twice per
+// iteration, and both applications read the SAME twelve coefficient / source arrays.  A single
+// sweep moves 56 B per point (himenobmtxpa_physis.c:418-432) of which 48 are those arrays;
+// computing sweep n+1 and n+2 of a tile while it is on the SM moves them once per two updates:
+// 12 x 4 + 4 (p read) + 4 (p write) = 56 B per TWO updates.  Every point sees exactly the
+// arithmetic of himeno.cu (HimenoJacobi, separately rounded fp32 in source order), so the result
+// is bit-identical to two separate sweeps.
+//
+// What the intermediate field looks like.  A Himeno sweep writes the interior [1, n-1)^3 only;
+// the boundary cells of the grid it writes keep what they held.  Pass "X -> Y" therefore needs
+// the boundary cells of Y as the boundary of the intermediate field.  The schedule
+// (stencil_run.cu) runs fused passes only while the boundary cells of both grids are bit-equal
+// (checked on the device, HimenoFacesEqual) -- the benchmark initialises both grids identically
+// for this very reason (himenobmtxpa_physis.c:138-139) -- so the intermediate's boundary is read
+// from X, which is on the SM anyway.
+//
+// Structure
+//  * a tile is one box of 128 floats (+ 16-byte x halo, as himeno.cu) x H rows, one row per
+//    warp; a CTA marches it along a z chunk.  First-sweep values ("s1") are computed on all H
+//    rows and all 128 columns, second-sweep values are stored for the H-2 inner rows and the
+//    tile's own columns: tiles overlap by two rows in y and by one 16-byte vector per seam side
+//    in x, chunks by two planes in z (the redundant work; the re-read rows / columns hit in L2);
+//  * p planes (H+2 rows) arrive by TMA in a 5-slot shared-memory ring, completion on mbarriers;
+//    s1 planes live in a 4-slot shared-memory ring of the same geometry (the second sweep reads
+//    its neighbours' cells in three s1 planes, so a slot is recycled one step later than in the
+//    7-point pair);
+//  * one CTA-wide barrier per plane orders both rings; thread 0 re-arms the p slot behind it;
+//  * the coefficient rows are pulled towards the SM by bulk L2 prefetches a few planes ahead
+//    (no registers held), the first sweep reads them with ordinary loads and the second sweep
+//    one step later again (L1 / L2 hits) with evict-first loads.
+#include "runtime.h"
+#include "tma.cuh"
+#include "sweep_common.cuh"
+#include "himeno_math.cuh"
+
+#include <algorithm>
+#include <string>
+
+namespace physis_b200 {
+
+namespace {
+
+using namespace sweep;
+
+constexpr int kHpMaxXTiles = 32;
+constexpr int kHpInSlots = 5;
+constexpr int kHpS1Slots = 4;
+
+struct HimenoPairArgs {
+  const float *coef[12];  // a0 a1 a2 a3 b0 b1 b2 c0 c1 c2 bnd wrk1
+  float *out;
+  float omega;
+  int nx, ny, nz;
+  int nty, ntx, nzc, zc, nitems;
+  int tx0[kHpMaxXTiles], txs[kHpMaxXTiles], txe[kHpMaxXTiles];
+  int dz0, dz1;  // planes written: [1, nz-1)
+  int pf;        // coefficient prefetch distance in planes
+};
+
+__device__ __forceinline__ void PrefetchL2(const void *p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+template <int H>
+struct HpGeom {
+  static constexpr int ROWB = Geom<float>::ROW_BYTES;                  // 544
+  static constexpr int STAGE = ((H + 2) * ROWB + 127) / 128 * 128;
+  static constexpr int SMEM = kBarrierBytes + (kHpInSlots + kHpS1Slots) * STAGE;
+};
+
+// H rows per tile = consumer warps; no producer warp (thread 0 issues the TMA loads).
+template <int H>
+__global__ void __launch_bounds__(H * 32, 1)
+HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ HimenoPairArgs a) {
+  using G = Geom<float>;
+  using PG = HpGeom<H>;
+  constexpr int VEC = 4;
+  constexpr int ROWB = PG::ROWB;
+  constexpr int STAGE = PG::STAGE;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+  unsigned char *in_ring = smem + kBarrierBytes;
+  unsigned char *s1_ring = in_ring + kHpInSlots * STAGE;
+
+  const int warp = threadIdx.x >> 5;  // tile row
+  const int lane = threadIdx.x & 31;
+  const bool issuer = (threadIdx.x == 0);
+
+  if (issuer) {
+    for (int s = 0; s < kHpInSlots; ++s) tma::mbar_init(&full[s], 1);
+    tma::fence_barrier_init();
+    tma::prefetch_tensormap(&tmap);
+  }
+
+  // this thread's vector inside a stage: row warp+1 (row 0 is the halo row above the tile),
+  // column 16 bytes of x halo + lane * 16
+  const int my_off = (warp + 1) * ROWB + (G::HX + lane * VEC) * (int)sizeof(float);
+  const size_t plane_elems = (size_t)a.nx * a.ny;
+  const int tiles_xy = a.nty * a.ntx;
+  uint32_t par = 0;  // bit s: phase parity of p slot s
+
+  auto vec = [](const unsigned char *row, int dy) {
+    return *reinterpret_cast<const float4 *>(row + dy * ROWB);
+  };
+  auto west = [](const unsigned char *row, int dy) {
+    return *reinterpret_cast<const float *>(row + dy * ROWB - 4);
+  };
+  auto east = [](const unsigned char *row, int dy) {
+    return *reinterpret_cast<const float *>(row + dy * ROWB + 16);
+  };
+
+  for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+    const int zci = item / tiles_xy;
+    const int txy = item - zci * tiles_xy;
+    const int ty = txy / a.ntx;
+    const int tx = txy - ty * a.ntx;
+    const int xt0 = a.tx0[tx];
+    const int x = xt0 + lane * VEC;
+    const int y = ty * (H - 2) + warp;  // grid row of this warp's tile row
+    const int zb = a.dz0 + zci * a.zc;
+    const int ze = min(zb + a.zc, a.dz1);
+    const int kfirst = zb - 2;   // first p plane of the window (may be -1: zero fill, unused)
+    const int klast = ze + 1;    // last p plane of the window (may be nz: zero fill, unused)
+    const bool row_in_grid = (y < a.ny);
+    const bool row_bnd = (y == 0) || (y >= a.ny - 1);
+    // cells of this vector that the sweeps update (the rest keep the input value)
+    bool upd[VEC], st[VEC];
+    const bool st_row = (warp >= 1) && (warp <= H - 2) && (y >= 1) && (y < a.ny - 1);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      upd[j] = (x + j >= 1) && (x + j < a.nx - 1);
+      st[j] = st_row && upd[j] && (x + j >= a.txs[tx]) && (x + j < a.txe[tx]);
+    }
+    const bool st_any = st[0] || st[1] || st[2] || st[3];
+    const bool st_all = st[0] && st[1] && st[2] && st[3];
+    const bool ld_row = row_in_grid && !row_bnd && (x < a.nx);  // the row computes first-sweep values
+    // offset of this thread's vector inside a plane of the coefficient arrays / of `out`
+    const size_t gp = (size_t)y * a.nx + x;
+
+    // every thread is done with both rings of the previous item
+    __syncthreads();
+    if (issuer) {
+      for (int n = 0; n < kHpInSlots; ++n) {
+        const int q = kfirst + n;
+        if (q <= klast) {
+          tma::mbar_arrive_expect_tx(&full[n], (uint32_t)((H + 2) * ROWB));
+          tma::load_3d(in_ring + n * STAGE, &tmap, &full[n], xt0 - G::HX, ty * (H - 2) - 1, q);
+        }
+      }
+    }
+    // pull the coefficient rows of the first planes towards L2 (one array per lane)
+    if (lane < 12 && ld_row) {
+      const uint32_t bytes = (uint32_t)min(G::TXB, a.nx - xt0) * 4u;
+      for (int m = max(zb - 1, 1); m < min(zb - 1 + a.pf, a.nz - 1); ++m)
+        PrefetchL2(a.coef[lane] + (size_t)m * plane_elems + (size_t)y * a.nx + xt0, bytes);
+    }
+
+    int slot_b = 0;  // p slot of plane k (bottom of the first sweep's window)
+    // planes kfirst and kfirst+1 are waited for here, plane k+2 inside the loop
+    tma::mbar_wait(&full[0], (par >> 0) & 1u);
+    par ^= 1u << 0;
+    tma::mbar_wait(&full[1], (par >> 1) & 1u);
+    par ^= 1u << 1;
+
+    for (int k = kfirst; k < ze; ++k) {
+      const int m = k + 1;  // plane whose first-sweep values this step computes
+      const int slot_c = (slot_b + 1 == kHpInSlots) ? 0 : slot_b + 1;
+      const int slot_t = (slot_c + 1 == kHpInSlots) ? 0 : slot_c + 1;
+      const bool plane_upd = (m >= 1) && (m < a.nz - 1);
+      const size_t gm = (size_t)m * plane_elems + gp;
+      // ---- first sweep: s1(m) from p(m-1), p(m), p(m+1) ---------------------------------
+      float4 q0, q1, q2, q3, q4, q5, q6, q7, q8, q9, q10, q11;
+      const bool compute1 = ld_row && plane_upd;
+      if (compute1) {
+        q0 = __ldg(reinterpret_cast<const float4 *>(a.coef[0] + gm));
+        q1 = __ldg(reinterpret_cast<const float4 *>(a.coef[1] + gm));
+        q2 = __ldg(reinterpret_cast<const float4 *>(a.coef[2] + gm));
+        q3 = __ldg(reinterpret_cast<const float4 *>(a.coef[3] + gm));
+        q4 = __ldg(reinterpret_cast<const float4 *>(a.coef[4] + gm));
+        q5 = __ldg(reinterpret_cast<const float4 *>(a.coef[5] + gm));
+        q6 = __ldg(reinterpret_cast<const float4 *>(a.coef[6] + gm));
+        q7 = __ldg(reinterpret_cast<const float4 *>(a.coef[7] + gm));
+        q8 = __ldg(reinterpret_cast<const float4 *>(a.coef[8] + gm));
+        q9 = __ldg(reinterpret_cast<const float4 *>(a.coef[9] + gm));
+        q10 = __ldg(reinterpret_cast<const float4 *>(a.coef[10] + gm));
+        q11 = __ldg(reinterpret_cast<const float4 *>(a.coef[11] + gm));
+        // and the row of plane m + pf towards L2
+        const int mp = m + a.pf;
+        if (lane < 12 && mp < a.nz - 1 && mp <= ze)
+          PrefetchL2(a.coef[lane] + (size_t)mp * plane_elems + (size_t)y * a.nx + xt0,
+                     (uint32_t)min(G::TXB, a.nx - xt0) * 4u);
+      }
+      tma::mbar_wait(&full[slot_t], (par >> slot_t) & 1u);
+      par ^= 1u << slot_t;
+      {
+        const unsigned char *pb = in_ring + slot_b * STAGE + my_off;
+        const unsigned char *pc = in_ring + slot_c * STAGE + my_off;
+        const unsigned char *pt = in_ring + slot_t * STAGE + my_off;
+        const float4 c_c = vec(pc, 0);
+        float4 o = c_c;  // cells the sweep does not update keep the input value
+        if (compute1) {
+          const float4 c_n = vec(pc, -1), c_s = vec(pc, 1);
+          const float c_cw = west(pc, 0), c_ce = east(pc, 0);
+          const float c_nw = west(pc, -1), c_ne = east(pc, -1);
+          const float c_sw = west(pc, 1), c_se = east(pc, 1);
+          const float4 b_c = vec(pb, 0), b_n = vec(pb, -1), b_s = vec(pb, 1);
+          const float b_w = west(pb, 0), b_e = east(pb, 0);
+          const float4 t_c = vec(pt, 0), t_n = vec(pt, -1), t_s = vec(pt, 1);
+          const float t_w = west(pt, 0), t_e = east(pt, 0);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            const float c_xm = (j == 0) ? c_cw : Elem(c_c, j - 1);
+            const float c_xp = (j == VEC - 1) ? c_ce : Elem(c_c, j + 1);
+            const float n_xm = (j == 0) ? c_nw : Elem(c_n, j - 1);
+            const float n_xp = (j == VEC - 1) ? c_ne : Elem(c_n, j + 1);
+            const float s_xm = (j == 0) ? c_sw : Elem(c_s, j - 1);
+            const float s_xp = (j == VEC - 1) ? c_se : Elem(c_s, j + 1);
+            const float b_xm = (j == 0) ? b_w : Elem(b_c, j - 1);
+            const float b_xp = (j == VEC - 1) ? b_e : Elem(b_c, j + 1);
+            const float t_xm = (j == 0) ? t_w : Elem(t_c, j - 1);
+            const float t_xp = (j == VEC - 1) ? t_e : Elem(t_c, j + 1);
+            float ss;
+            const float v = HimenoJacobi(
+                Elem(q0, j), Elem(q1, j), Elem(q2, j), Elem(q3, j), Elem(q4, j), Elem(q5, j),
+                Elem(q6, j), Elem(q7, j), Elem(q8, j), Elem(q9, j), Elem(q10, j), Elem(q11, j),
+                a.omega,
+                Elem(c_c, j), Elem(t_c, j), Elem(c_s, j), c_xp,
+                Elem(t_s, j), Elem(t_n, j), Elem(b_s, j), Elem(b_n, j),
+                s_xp, n_xp, s_xm, n_xm,
+                t_xp, b_xp, t_xm, b_xm,
+                Elem(b_c, j), Elem(c_n, j), c_xm, &ss);
+            if (upd[j]) SetElem(o, j, v);
+          }
+        }
+        *reinterpret_cast<float4 *>(s1_ring + (m & (kHpS1Slots - 1)) * STAGE + my_off) = o;
+      }
+      __syncthreads();
+      if (issuer) {
+        // nobody reads p plane k any more: its slot takes plane k + kHpInSlots
+        const int q = k + kHpInSlots;
+        if (q <= klast) {
+          tma::mbar_arrive_expect_tx(&full[slot_b], (uint32_t)((H + 2) * ROWB));
+          tma::load_3d(in_ring + slot_b * STAGE, &tmap, &full[slot_b], xt0 - G::HX, ty * (H - 2) - 1, q);
+        }
+      }
+      // ---- second sweep: out(k) from s1(k-1), s1(k), s1(k+1) ------------------------------
+      if (k >= zb && st_any) {
+        const size_t gk = (size_t)k * plane_elems + gp;
+        const float4 r0 = __ldcs(reinterpret_cast<const float4 *>(a.coef[0] + gk));
+        const float4 r1 = __ldcs(reinterpret_cast<const float4 *>(a.coef[1] + gk));
+        const float4 r2 = __ldcs(reinterpret_cast<const float4 *>(a.coef[2] + gk));
+        const float4 r3 = __ldcs(reinterpret_cast<const float4 *>(a.coef[3] + gk));
+        const float4 r4 = __ldcs(reinterpret_cast<const float4 *>(a.coef[4] + gk));
+        const float4 r5 = __ldcs(reinterpret_cast<const float4 *>(a.coef[5] + gk));
+        const float4 r6 = __ldcs(reinterpret_cast<const float4 *>(a.coef[6] + gk));
+        const float4 r7 = __ldcs(reinterpret_cast<const float4 *>(a.coef[7] + gk));
+        const float4 r8 = __ldcs(reinterpret_cast<const float4 *>(a.coef[8] + gk));
+        const float4 r9 = __ldcs(reinterpret_cast<const float4 *>(a.coef[9] + gk));
+        const float4 r10 = __ldcs(reinterpret_cast<const float4 *>(a.coef[10] + gk));
+        const float4 r11 = __ldcs(reinterpret_cast<const float4 *>(a.coef[11] + gk));
+        const unsigned char *pb = s1_ring + ((k - 1) & (kHpS1Slots - 1)) * STAGE + my_off;
+        const unsigned char *pc = s1_ring + (k & (kHpS1Slots - 1)) * STAGE + my_off;
+        const unsigned char *pt = s1_ring + ((k + 1) & (kHpS1Slots - 1)) * STAGE + my_off;
+        const float4 c_c = vec(pc, 0), c_n = vec(pc, -1), c_s = vec(pc, 1);
+        const float c_cw = west(pc, 0), c_ce = east(pc, 0);
+        const float c_nw = west(pc, -1), c_ne = east(pc, -1);
+        const float c_sw = west(pc, 1), c_se = east(pc, 1);
+        const float4 b_c = vec(pb, 0), b_n = vec(pb, -1), b_s = vec(pb, 1);
+        const float b_w = west(pb, 0), b_e = east(pb, 0);
+        const float4 t_c = vec(pt, 0), t_n = vec(pt, -1), t_s = vec(pt, 1);
+        const float t_w = west(pt, 0), t_e = east(pt, 0);
+        float4 o;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float c_xm = (j == 0) ? c_cw : Elem(c_c, j - 1);
+          const float c_xp = (j == VEC - 1) ? c_ce : Elem(c_c, j + 1);
+          const float n_xm = (j == 0) ? c_nw : Elem(c_n, j - 1);
+          const float n_xp = (j == VEC - 1) ? c_ne : Elem(c_n, j + 1);
+          const float s_xm = (j == 0) ? c_sw : Elem(c_s, j - 1);
+          const float s_xp = (j == VEC - 1) ? c_se : Elem(c_s, j + 1);
+          const float b_xm = (j == 0) ? b_w : Elem(b_c, j - 1);
+          const float b_xp = (j == VEC - 1) ? b_e : Elem(b_c, j + 1);
+          const float t_xm = (j == 0) ? t_w : Elem(t_c, j - 1);
+          const float t_xp = (j == VEC - 1) ? t_e : Elem(t_c, j + 1);
+          float ss;
+          const float v = HimenoJacobi(
+              Elem(r0, j), Elem(r1, j), Elem(r2, j), Elem(r3, j), Elem(r4, j), Elem(r5, j),
+              Elem(r6, j), Elem(r7, j), Elem(r8, j), Elem(r9, j), Elem(r10, j), Elem(r11, j),
+              a.omega,
+              Elem(c_c, j), Elem(t_c, j), Elem(c_s, j), c_xp,
+              Elem(t_s, j), Elem(t_n, j), Elem(b_s, j), Elem(b_n, j),
+              s_xp, n_xp, s_xm, n_xm,
+              t_xp, b_xp, t_xm, b_xm,
+              Elem(b_c, j), Elem(c_n, j), c_xm, &ss);
+          SetElem(o, j, v);
+        }
+        if (st_all) {
+          __stcs(reinterpret_cast<float4 *>(a.out + gk), o);
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j)
+            if (st[j]) a.out[gk + j] = Elem(o, j);
+        }
+      }
+      slot_b = slot_c;
+    }
+  }
+}
+
+// 1 where a boundary cell of the two grids differs (bitwise), else untouched
+__global__ void HimenoFacesDifferKernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                                        int nx, int ny, int nz, int *flag) {
+  const long nxy = (long)nx * ny, nxz = (long)nx * nz, nyz = (long)ny * nz;
+  const long total = 2 * (nxy + nxz + nyz);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    int x, y, z;
+    if (r < 2 * nxy) {
+      z = (r >= nxy) ? nz - 1 : 0;
+      r %= nxy;
+      y = (int)(r / nx);
+      x = (int)(r % nx);
+    } else if ((r -= 2 * nxy) < 2 * nxz) {
+      y = (r >= nxz) ? ny - 1 : 0;
+      r %= nxz;
+      z = (int)(r / nx);
+      x = (int)(r % nx);
+    } else {
+      r -= 2 * nxz;
+      x = (r >= nyz) ? nx - 1 : 0;
+      r %= nyz;
+      z = (int)(r / ny);
+      y = (int)(r % ny);
+    }
+    const size_t off = ((size_t)z * ny + y) * nx + x;
+    if (a[off] != b[off]) *flag = 1;
+  }
+}
+
+}  // namespace
+
+struct HimenoPairPlan {
+  int grid = 0, block = 0;
+  size_t smem = 0;
+  const void *fn = nullptr;
+  CUtensorMap tmap[2];  // direction 0 reads the first grid, direction 1 the second
+  HimenoPairArgs args[2];
+  Grid *g[2] = {nullptr, nullptr};
+};
+
+// d0: X -> Y, d1: Y -> X, both the Himeno sweep over the interior with the same coefficient
+// grids and omega.  Returns nullptr (with a reason) when the pair cannot be fused.
+HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
+                                  const __PSB200StencilDesc &d1, std::string *why) {
+  const Options &o = rt->opt;
+  if (!o.himeno_fuse) { *why = "himeno_fuse=0"; return nullptr; }
+  const bool k0 = d0.kind == PSB200_KIND_HIMENO19 || d0.kind == PSB200_KIND_HIMENO19_GOSA;
+  const bool k1 = d1.kind == PSB200_KIND_HIMENO19 || d1.kind == PSB200_KIND_HIMENO19_GOSA;
+  if (!k0 || !k1 || d0.kind != d1.kind) { *why = "not a pair of Himeno sweeps"; return nullptr; }
+  const int ng = d0.kind == PSB200_KIND_HIMENO19_GOSA ? 15 : 14;
+  if (d0.num_grids != ng || d1.num_grids != ng || d0.num_scalars != 1 || d1.num_scalars != 1) {
+    *why = "expects 14(+1) grids and omega"; return nullptr;
+  }
+  if (d0.grids[0] != d1.grids[1] || d0.grids[1] != d1.grids[0] || d0.grids[0] == d0.grids[1]) {
+    *why = "the sweeps do not ping-pong between two grids"; return nullptr;
+  }
+  for (int i = 2; i < ng; ++i)
+    if (d0.grids[i] != d1.grids[i]) { *why = "the sweeps use different coefficient grids"; return nullptr; }
+  if (d0.scalars[0] != d1.scalars[0]) { *why = "the sweeps use different omega"; return nullptr; }
+  if (rt->world() > 1) { *why = "fused Himeno passes run on one GPU only"; return nullptr; }
+  Grid *g[15];
+  for (int i = 0; i < ng; ++i) {
+    g[i] = Grid::FromHandle(d0.grids[i]);
+    if (g[i]->num_dims != 3 || g[i]->type != PS_FLOAT) { *why = "3-D float grids only"; return nullptr; }
+    for (int k = 0; k < 3; ++k)
+      if (g[i]->dim[k] != g[0]->dim[k]) { *why = "grids must have equal extents"; return nullptr; }
+  }
+  // neither p grid may double as a coefficient (or residual) grid
+  for (int i = 2; i < ng; ++i)
+    if (g[i] == g[0] || g[i] == g[1]) { *why = "a p grid is also a coefficient grid"; return nullptr; }
+  const int nx = g[0]->dim[0], ny = g[0]->dim[1], nz = g[0]->dim[2];
+  if (nx % 4 != 0) { *why = "x extent must be a multiple of 4"; return nullptr; }
+  if (nx < 8 || ny < 3 || nz < 3) { *why = "grid too small"; return nullptr; }
+  for (int s = 0; s < 2; ++s) {
+    const __PSDomain &dom = s ? d1.dom : d0.dom;
+    for (int i = 0; i < 3; ++i)
+      if (dom.local_min[i] != 1 || dom.local_max[i] != g[0]->dim[i] - 1) {
+        *why = "both sweeps must cover exactly the interior"; return nullptr;
+      }
+  }
+  constexpr int H = 16;
+  HimenoPairPlan *p = new HimenoPairPlan();
+  p->fn = (const void *)HimenoPairKernel<H>;
+  p->smem = HpGeom<H>::SMEM;
+  p->block = H * 32;
+  p->g[0] = g[0];
+  p->g[1] = g[1];
+  PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+  // shared memory: just the rings; the rest of the SM's array stays L1, which is where the
+  // second sweep finds the coefficient rows the first sweep read one step earlier
+  {
+    const int pct = (int)(((p->smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(pct, 100)));
+  }
+  int occ = 0;
+  PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->fn, p->block, p->smem));
+  PSB_CHECK(occ > 0, "fused himeno kernel does not fit on an SM");
+  const int slots = rt->sm_count * occ;
+
+  // x tiles: 128 columns loaded per tile (+ halo), the tile's own columns stored; one vector
+  // per seam side is recomputed by the neighbour
+  const int w = Geom<float>::TXB;
+  int ntx = 1, seg = nx;
+  if (nx > w) {
+    for (ntx = 2; ntx <= kHpMaxXTiles; ++ntx) {
+      seg = CeilDiv(CeilDiv(nx, ntx), 4) * 4;
+      if (seg + 8 <= w) break;
+    }
+    if (ntx > kHpMaxXTiles) { *why = "rows wider than 32 x tiles"; delete p; return nullptr; }
+  }
+  const int nty = CeilDiv(ny - 2, H - 2);
+  const int nzd = nz - 2;
+  int zc = o.himeno_pair_zc;
+  if (zc <= 0) {
+    // every chunk re-reads 4 planes and recomputes 2 first-sweep planes; items run in waves
+    long best = -1;
+    for (int n = 1; n <= std::max(1, nzd / 4); ++n) {
+      const int c = CeilDiv(nzd, n);
+      const long waves = CeilDiv((long)nty * ntx * CeilDiv(nzd, c), slots);
+      const long cost = waves * (c + 3);
+      if (best < 0 || cost < best) { best = cost; zc = c; }
+    }
+  }
+  zc = std::max(1, std::min(zc, nzd));
+  const int nzc = CeilDiv(nzd, zc);
+  for (int dir = 0; dir < 2; ++dir) {
+    int dimv[3] = {nx, ny, nz};
+    int boxv[3] = {Geom<float>::BW, H + 2, 1};
+    if (!EncodeTensorMap3D(&p->tmap[dir], TmaElem::F32, g[dir]->members[0].dev, dimv, boxv)) {
+      *why = "grid shape violates a TMA constraint";
+      delete p;
+      return nullptr;
+    }
+    HimenoPairArgs &a = p->args[dir];
+    // descriptor grid order: p0,p1,a0..a3,b0..b2,c0..c2,bnd,wrk1[,gosa]
+    for (int i = 0; i < 12; ++i) a.coef[i] = (const float *)g[2 + i]->members[0].dev;
+    a.out = (float *)g[1 - dir]->members[0].dev;
+    a.omega = (float)d0.scalars[0];
+    a.nx = nx; a.ny = ny; a.nz = nz;
+    a.nty = nty; a.ntx = ntx; a.nzc = nzc; a.zc = zc;
+    a.nitems = nty * ntx * nzc;
+    for (int t = 0; t < ntx; ++t) {
+      a.txs[t] = std::min(t * seg, nx);
+      a.txe[t] = std::min((t + 1) * seg, nx);
+      a.tx0[t] = ntx == 1 ? 0 : std::max(0, std::min(a.txs[t] - 4, nx - w));
+    }
+    a.dz0 = 1;
+    a.dz1 = nz - 1;
+    a.pf = std::max(1, std::min(o.himeno_pair_pf, 8));
+  }
+  p->grid = std::min(p->args[0].nitems, slots);
+  return p;
+}
+
+// true when the boundary cells of the pair's two grids are bit-equal (a fused pass takes the
+// intermediate field's boundary from the grid it reads).  Synchronises the stream.
+bool HimenoPairFacesEqual(Runtime *rt, HimenoPairPlan *p) {
+  DeviceBuffer &scr = rt->small_scratch(sizeof(int));
+  int *flag = (int *)scr.get();
+  PSB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), rt->stream));
+  const HimenoPairArgs &a = p->args[0];
+  HimenoFacesDifferKernel<<<rt->sm_count * 2, 256, 0, rt->stream>>>(
+      (const uint32_t *)p->g[0]->members[0].dev, (const uint32_t *)p->g[1]->members[0].dev, a.nx, a.ny,
+      a.nz, flag);
+  PSB_CUDA(cudaGetLastError());
+  rt->stats.kernel_launches++;
+  int differ = 0;
+  PSB_CUDA(cudaMemcpyAsync(&differ, flag, sizeof(int), cudaMemcpyDeviceToHost, rt->stream));
+  PSB_CUDA(cudaStreamSynchronize(rt->stream));
+  return differ == 0;
+}
+
+void LaunchHimenoPair(Runtime *rt, HimenoPairPlan *p, int dir) {
+  void *args[2] = {&p->tmap[dir], &p->args[dir]};
+  PSB_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(p->block), args, p->smem, rt->stream));
+}
+
+void DestroyHimenoPair(HimenoPairPlan *p) { delete p; }
+
+}  // namespace physis_b200

@@ -78,6 +78,7 @@ void Runtime::InitGroup() {
   if ((!g_wait32 || !g_write32) && opt.sync_mode == 0) opt.sync_mode = 1;
   sweep_epoch = 0;
   done_counter = reinterpret_cast<unsigned *>(flags + 16);  // same zeroed allocation
+  halo_prof = reinterpret_cast<unsigned long long *>(flags + 32);  // same zeroed allocation
   void *e = nullptr;
   PSB_CUDA(cudaHostAlloc(&e, 64, cudaHostAllocMapped));
   memset(e, 0, 64);
@@ -93,6 +94,7 @@ bool Runtime::FillSlabSync(sweep::SlabSync *s) {
   s->done = done_counter;
   s->timeout_ns = (unsigned long long)std::max(1, opt.sync_timeout_s) * 1000000000ull;
   s->err = const_cast<uint32_t *>(dev_err);
+  s->prof = opt.halo_profile ? halo_prof : nullptr;
   return true;
 }
 

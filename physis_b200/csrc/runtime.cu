@@ -216,6 +216,7 @@ Grid *GridSpace::Create(const __PSGridTypeInfo *ti, int num_dims, const int *dim
 }
 
 void GridSpace::Destroy(Grid *g) {
+  ClearPlanCache();  // plans hold this grid's device addresses
   grids_.erase(g->id);
   if (g->decomposed) {
     Runtime *rt = Runtime::Get();
@@ -330,6 +331,7 @@ void Runtime::Destroy() {
   if (!g_rt) return;
   if (g_rt->stream) cudaStreamSynchronize(g_rt->stream);
   if (g_rt->comm && g_rt->world() > 1) g_rt->comm->Barrier();  // nobody still writes my halos
+  ClearPlanCache();
   g_rt->gs.Clear();
   g_rt->ShutdownGroup();
   delete g_rt;
@@ -459,12 +461,18 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "star7_sthint") o->star7_sthint = (int)val;
   else if (k == "star7_fuse") o->star7_fuse = (int)val;
   else if (k == "star7_pair_zc") o->star7_pair_zc = (int)val;
+  else if (k == "star7_pair_xtile") o->star7_pair_xtile = (int)val;
+  else if (k == "star7_pair_zbl") o->star7_pair_zbl = (int)val;
+  else if (k == "star7_pair_variant") o->star7_pair_variant = (int)val;
   else if (k == "star7_iso") o->star7_iso = (int)val;
   else if (k == "himeno_by") o->himeno_by = (int)val;
   else if (k == "himeno_zc") o->himeno_zc = (int)val;
   else if (k == "himeno_stages") o->himeno_stages = (int)val;
   else if (k == "himeno_occ") o->himeno_occ = (int)val;
   else if (k == "himeno_carveout") o->himeno_carveout = (int)val;
+  else if (k == "himeno_fuse") o->himeno_fuse = (int)val;
+  else if (k == "himeno_pair_zc") o->himeno_pair_zc = (int)val;
+  else if (k == "himeno_pair_pf") o->himeno_pair_pf = (int)val;
   else if (k == "pstag_variant") o->pstag_variant = (int)val;
   else if (k == "pstag_stages") o->pstag_stages = (int)val;
   else if (k == "pstag_occ") o->pstag_occ = (int)val;
@@ -478,6 +486,8 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "early_signal") o->early_signal = (int)val;
   else if (k == "sync_timeout_s") o->sync_timeout_s = (int)val;
   else if (k == "reduce_fuse") o->reduce_fuse = (int)val;
+  else if (k == "plan_cache") o->plan_cache = (int)val;
+  else if (k == "halo_profile") o->halo_profile = (int)val;
   else return -1;
   return 0;
 }
@@ -568,6 +578,7 @@ void __PSGridFree(void *gv, __PSGrid_devFreeFunc func) {
   Grid *g = Grid::FromHandle(gv);
   PSB_CUDA(cudaStreamSynchronize(rt->stream));
   if (g->decomposed) rt->comm->Barrier();  // neighbours are done writing this grid's halos
+  rt->group_dirty = true;
   if (g->external_dev) {
     if (func && g->handle.dev) func(g->handle.dev);
     delete g;
@@ -649,6 +660,7 @@ void __PSGridCopyin(void *gv, const void *src, __PSGrid_devCopyinFunc func) {
   }
   PSB_CHECK(!g->external_dev, "copyin of an externally allocated grid needs its helper");
   g->NoteUnknownWrite();
+  rt->group_dirty = true;
   if (g->decomposed) {
     // every rank holds the same global host array (SPMD): take this rank's slab and
     // its halo planes straight from it -- no inter-GPU traffic.  The barrier makes
@@ -698,6 +710,7 @@ void __PSB200GridCopyinLocal(void *gv, const void *src) {
   Runtime *rt = Runtime::Get();
   Grid *g = Grid::FromHandle(gv);
   g->NoteUnknownWrite();
+  rt->group_dirty = true;
   PSB_CUDA(cudaStreamSynchronize(rt->stream));
   if (g->decomposed) rt->comm->Barrier();
   SlabSeg seg = {0, g->halo, g->nz_loc};
@@ -769,6 +782,7 @@ void __PSGridSet(__PSGrid *gh, void *buf, ...) {
   Runtime *rt = Runtime::Get();
   Grid *g = Grid::FromHandle(gh);
   g->NoteUnknownWrite();
+  rt->group_dirty = true;
   va_list vl;
   va_start(vl, buf);
   PSIndex idx[PS_MAX_DIM] = {0, 0, 0};
@@ -858,14 +872,27 @@ void __PSB200GetStats(__PSB200Stats *out) {
   Runtime *rt = Runtime::Get();
   *out = rt->stats;
   out->last_kernel_ms = rt->timed_launches ? (float)(rt->timed_ms / rt->timed_launches) : 0.f;
+  if (rt->halo_prof && rt->opt.halo_profile) {
+    unsigned long long w[4] = {0, 0, 0, 0};
+    PSB_CUDA(cudaMemcpyAsync(w, rt->halo_prof, sizeof w, cudaMemcpyDeviceToHost, rt->stream));
+    PSB_CUDA(cudaStreamSynchronize(rt->stream));
+    out->halo_wait_ns_sum = w[0];
+    out->halo_wait_ns_max = w[1];
+    out->halo_wait_ctas = w[2];
+    out->halo_wait_launches = w[3];
+  }
 }
 void __PSB200ResetStats(void) {
   Runtime *rt = Runtime::Get();
   rt->stats = __PSB200Stats{};
+  if (rt->halo_prof) PSB_CUDA(cudaMemsetAsync(rt->halo_prof, 0, 4 * sizeof(unsigned long long), rt->stream));
   rt->timed_ms = 0;
   rt->timed_launches = 0;
 }
-int __PSB200SetOption(const char *kv) { return ParseKV(&Runtime::Get()->opt, kv); }
+int __PSB200SetOption(const char *kv) {
+  ClearPlanCache();  // plans bake option-dependent choices in
+  return ParseKV(&Runtime::Get()->opt, kv);
+}
 const char *__PSB200Version(void) { return "physis-b200 0.1 (sm_100a)"; }
 
 void *__PSB200HostAlloc(size_t bytes) {

@@ -168,8 +168,14 @@ struct Options {
   int star7_variant = -1 /* auto */, star7_l2hint = 0, star7_sthint = 0, star7_impl = 2;
   int star7_fuse = 1;     // 1: a ping-pong pair of whole-grid 7-pt sweeps runs as one fused two-sweep pass
   int star7_pair_zc = 0;  // z chunk of the fused kernel; 0 = automatic
+  int star7_pair_zbl = 8;       // multi-GPU: planes of the boundary chunks that run first (0: equal chunks)
+  int star7_pair_xtile = 1;     // 1: rows wider than one fused tile are cut into x tiles
+  int star7_pair_variant = -1;  // tile shape of the x-tiled form; -1 = automatic
   int star7_iso = 1;      // 1: equal neighbour coefficients use the shared-product form of the fused kernel
   int himeno_by = 0, himeno_zc = 0, himeno_stages = 0, himeno_occ = 0, himeno_carveout = 0;
+  int himeno_fuse = 1;      // 1: a ping-pong pair of interior Himeno sweeps runs as fused two-sweep passes
+  int himeno_pair_zc = 0;   // z chunk of the fused Himeno kernel; 0 = automatic
+  int himeno_pair_pf = 2;   // planes ahead the coefficient rows are prefetched into L2
   int pstag_variant = 13 /* measured best, profiles/r1_tune_pstag_512.csv */, pstag_stages = 0, pstag_occ = 0;
   int time_kernels = 0;        // per-family CUDA-event timing (for bench roofline)
   size_t stage_chunk = 64u << 20;  // pinned staging chunk for pageable copies
@@ -186,6 +192,8 @@ struct Options {
                          // are done, so that the neighbours' next sweep overlaps the interior chunks
   int copyout_gather = 1;  // PSGridCopyout fills the whole host array on every rank
   int sync_timeout_s = 120;  // a neighbour silent for longer than this is a reported error
+  int plan_cache = 1;    // keep prepared sweep plans across PSStencilRun calls
+  int halo_profile = 0;  // 1: sweeps record how long their CTAs wait for the ring neighbours
   int reduce_fuse = 1;   // PSReduce(PS_SUM) folds the partial sums the producing sweep left (himeno.cu)
 };
 
@@ -231,10 +239,14 @@ class Runtime {
   uint32_t *flags_of_lo = nullptr;   // IPC mappings of the neighbours' flag words
   uint32_t *flags_of_hi = nullptr;
   uint32_t sweep_epoch = 0;          // sweeps enqueued so far (identical on every rank)
+  // a synchronous runtime call has written grids from the host since the last PSStencilRun:
+  // the next run starts with a host barrier (every rank takes the same decision: SPMD)
+  bool group_dirty = true;
   unsigned *done_counter = nullptr;  // finished-CTA counter of sweeps that signal themselves
   // host-mapped words a kernel writes when a neighbour's signal never arrives:
   // [0] = 1 + neighbour (0 lo, 1 hi), [1] = sweep waited for, [2] = last value seen, [3] = CTA
   volatile uint32_t *dev_err = nullptr;
+  unsigned long long *halo_prof = nullptr;  // device counters of the halo-exchange profile (4 words)
   // aborts with a message if a kernel reported a lost neighbour signal (call after a stream sync)
   void CheckDeviceErrors(const char *where);
   // fills the device-side view of the flag words for a kernel that waits / signals itself;
@@ -287,5 +299,8 @@ SweepPlan *PrepareSweep(Runtime *rt, const __PSB200StencilDesc &d);
 void LaunchSweep(Runtime *rt, SweepPlan *plan);
 void DestroySweep(SweepPlan *plan);
 const char *SweepName(const SweepPlan *plan);
+// prepared plans hold device addresses and option-dependent choices: dropped whenever a grid
+// is freed or an option changes
+void ClearPlanCache();
 
 }  // namespace physis_b200

@@ -11,10 +11,14 @@
 // result is bit-identical to two separate sweeps.
 //
 // Structure
-//  * a tile is NBX boxes wide = whole grid rows (no x halo) and H = NWY*RY rows high;
-//    a CTA marches it along a z chunk.  First-sweep values ("s1") are computed on all
-//    H rows, second-sweep values are stored for the H-2 inner rows; tiles overlap by
-//    two rows in y and chunks by two planes in z (the only redundant work);
+//  * a tile is NBX boxes wide and H = NWY*RY rows high; a CTA marches it along a z chunk.
+//    Rows of up to 4 boxes (512 fp32 / 256 fp64) are one tile wide: whole grid rows, no x
+//    halo.  Wider rows (BASELINE config 4: 1024 floats) are cut into x tiles that overlap
+//    by one 16-byte vector per seam side: first-sweep values ("s1") are computed on every
+//    column of a tile (the outermost column of a seam from a garbage neighbour, which no
+//    stored value depends on), second-sweep values are stored for the tile's own columns.
+//    In y, s1 is computed on all H rows and second-sweep values are stored for the H-2
+//    inner rows; tiles overlap by two rows in y and chunks by two planes in z;
 //  * input planes (H+2 rows) arrive by TMA (cp.async.bulk.tensor.3d, zero fill
 //    outside the grid) in a 3-slot shared-memory ring, completion on mbarriers.
 //    There is no producer warp: one CTA-wide barrier per plane already orders the
@@ -41,12 +45,24 @@ namespace {
 
 using namespace sweep;
 
+constexpr int kPairMaxXTiles = 16;
+
 template <typename T>
 struct PairArgs {
   T *out;
   int nx, ny, nz;        // extents of the (local) allocation; nz includes halo planes
   T cc, cw, ce, cs, cn, cb, ct;
   int nty, nzc, zc, nitems;
+  // z-slab schedule that lets the exchange overlap the interior (zbl > 0; multi-GPU only):
+  // chunk sequence 0 / 1 are the slab's first / last zbl planes -- the only chunks that read halo
+  // planes or feed the neighbours' -- then `nlong` chunks of `clong` planes and the rest in
+  // chunks of `cshort`.  The launch has one CTA per first-wave item, so the CTAs that took the
+  // short boundary chunks take the short interior chunks in the second wave and every CTA
+  // marches about the same number of planes.  zbl == 0: nzc equal chunks of zc planes.
+  int zbl, nlong, clong, cshort;
+  // x tiles: tile t loads columns [tx0[t], tx0[t] + NBX boxes) and stores [txs[t], txe[t])
+  int ntx;
+  int tx0[kPairMaxXTiles], txs[kPairMaxXTiles], txe[kPairMaxXTiles];
   int st_hint;
   // z-slab view (multi-GPU; on one GPU dz = [0, nz), the faces are planes 0 and nz-1 and
   // nothing is pushed).  Local plane indices throughout.
@@ -119,30 +135,10 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   unsigned char *my_s1 = const_cast<unsigned char *>(my_in) + NS * IN_STAGE;
   const bool rd_west = (lane == 0) && (bx > 0);
   const bool rd_east = (lane == 31) && (bx < NBX - 1);
-  const int x = bx * G::TXB + lane * VEC;
-  const bool x_ok = (x + VEC <= a.nx);
-  const bool x_first = (x == 0);
-  const bool x_last = (x + VEC == a.nx);
   const size_t plane_elems = (size_t)a.nx * a.ny;
-  int nbox = 0;
-#pragma unroll
-  for (int b = 0; b < NBX; ++b) nbox += (b * G::TXB < a.nx) ? 1 : 0;
-  const uint32_t tx_bytes = (uint32_t)nbox * (uint32_t)IN_BOX;
-
-  // x neighbours of a thread's vector come from shared memory (the centre plane of either
-  // sweep is there): the element before / after the vector, which for lane 0 / lane 31
-  // lives in the adjacent box and on a clamped x face is the vector's own edge element.
-  // One scalar load per side, no shuffles, no predicates.
-  const int w_in = x_first ? 0 : rd_west ? -IN_BOX + WEST_EL : -(int)sizeof(T);
-  const int e_in = x_last ? (VEC - 1) * (int)sizeof(T) : rd_east ? IN_BOX + EAST_EL : VEC * (int)sizeof(T);
   const T c6 = a.cw;
-  // ISO form: the raw x neighbours travel between lanes by shuffle (its shared-memory
-  // pipe is the busier one), only the lanes at a box edge load.  The offsets are made
-  // opaque so that they stay in registers instead of being recomputed under a branch.
   const bool need_w = (lane == 0);
-  const bool need_e = x_last || rd_east;
-  int w_edge = w_in, e_edge = e_in;
-  if (ISO) asm volatile("" : "+r"(w_edge), "+r"(e_edge));
+  const int tiles_xy = a.nty * a.ntx;
 
   uint32_t par = 0;  // bit s: phase parity of input slot s
   int pstage = 0;                          // issuer: slot the next plane is loaded into
@@ -167,7 +163,8 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     unsigned char *dst__ = in_ring + pstage * IN_STAGE; \
     const int zz__ = min(max((zpl), a.zld_lo), a.zld_hi); \
     _Pragma("unroll") for (int b = 0; b < NBX; ++b) \
-      if (b * G::TXB < a.nx) tma::load_3d(dst__ + b * IN_BOX, &tmap, &full[pstage], b * G::TXB, (yin), zz__); \
+      if (xt0 + b * G::TXB < a.nx) \
+        tma::load_3d(dst__ + b * IN_BOX, &tmap, &full[pstage], xt0 + b * G::TXB, (yin), zz__); \
     if (++pstage == NS) pstage = 0; \
   } while (0)
 
@@ -341,11 +338,49 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   } while (0)
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-    const int zseq = item / a.nty;
+    // x tiles of one (y tile, z chunk) are neighbours in the item order: they run at the same
+    // time and share their seam columns through L2
+    const int zseq = item / tiles_xy;
     const int zci = SLAB ? SlabChunkOrder(a.sync, zseq, a.nzc) : zseq;
-    const int ty = item - zseq * a.nty;
-    const int zb = a.dz0 + zci * a.zc;
-    const int ze = min(zb + a.zc, a.dz1);
+    const int txy = item - zseq * tiles_xy;
+    const int ty = txy / a.ntx;
+    const int tx = txy - ty * a.ntx;
+    const int xt0 = a.tx0[tx];                      // first column the tile loads
+    const int x = xt0 + bx * G::TXB + lane * VEC;   // this thread's vector
+    const bool x_ok = (x >= a.txs[tx]) && (x + VEC <= a.txe[tx]);
+    const bool x_first = (x == 0);
+    const bool x_last = (x + VEC == a.nx);
+    int nbox = 0;
+#pragma unroll
+    for (int b = 0; b < NBX; ++b) nbox += (xt0 + b * G::TXB < a.nx) ? 1 : 0;
+    const uint32_t tx_bytes = (uint32_t)nbox * (uint32_t)IN_BOX;
+    // x neighbours of a thread's vector come from shared memory (the centre plane of either
+    // sweep is there): the element before / after the vector, which for lane 0 / lane 31
+    // lives in the adjacent box and on a clamped x face is the vector's own edge element.
+    // One scalar load per side, no shuffles, no predicates.  (At a seam between x tiles the
+    // outermost lanes read a neighbour that is not theirs -- the row above's last element, or
+    // lane 0's by the shuffle: it reaches only the seam column's s1 value, which nothing stored
+    // depends on.)
+    const int w_in = x_first ? 0 : rd_west ? -IN_BOX + WEST_EL : -(int)sizeof(T);
+    const int e_in = x_last ? (VEC - 1) * (int)sizeof(T) : rd_east ? IN_BOX + EAST_EL : VEC * (int)sizeof(T);
+    // ISO form: the raw x neighbours travel between lanes by shuffle (its shared-memory
+    // pipe is the busier one), only the lanes at a box edge load.  The offsets are made
+    // opaque so that they stay in registers instead of being recomputed under a branch.
+    const bool need_e = x_last || rd_east;
+    int w_edge = w_in, e_edge = e_in;
+    if (ISO) asm volatile("" : "+r"(w_edge), "+r"(e_edge));
+    int zb = a.dz0 + zci * a.zc;
+    int ze = min(zb + a.zc, a.dz1);
+    if (SLAB && a.zbl > 0) {
+      if (zseq < 2) {
+        zb = zseq == 0 ? a.dz0 : a.dz1 - a.zbl;
+        ze = zb + a.zbl;
+      } else {
+        const int i = zseq - 2;
+        zb = a.dz0 + a.zbl + (i < a.nlong ? i * a.clong : a.nlong * a.clong + (i - a.nlong) * a.cshort);
+        ze = min(zb + (i < a.nlong ? a.clong : a.cshort), a.dz1 - a.zbl);
+      }
+    }
     const int k0 = (zb == a.zface_lo) ? zb - 1 : zb - 2;  // first plane of the input window
     const int y1 = ty * (H - 2) - 1;      // grid row of tile row 0
     const int ybase = y1 + j0;
@@ -444,7 +479,9 @@ const PairVariant kPairVariants[] = {
     PAIR_VARIANT(3, 4, 4, 1),  // 1
     PAIR_VARIANT(2, 4, 4, 2),  // 2
     PAIR_VARIANT(1, 4, 4, 4),  // 3
+    PAIR_VARIANT(3, 5, 4, 1),  // 4: x tiles of rows wider than 4 boxes, 20-row tiles (15 warps)
 };
+constexpr int kPairWideVariant = 4;
 constexpr int kNumPairVariants = sizeof(kPairVariants) / sizeof(kPairVariants[0]);
 
 }  // namespace
@@ -513,9 +550,22 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
   if (nx % vec != 0) { *why = "x extent must be a multiple of 16 bytes"; return nullptr; }
   const int boxes = CeilDiv(nx, txb);
   int variant = -1;
-  for (int v = 0; v < kNumPairVariants; ++v)
+  for (int v = 0; v < kPairWideVariant; ++v)
     if (kPairVariants[v].nbx == boxes) variant = v;
-  if (variant < 0) { *why = "rows wider than the fused kernel's tile"; return nullptr; }
+  // rows wider than 4 boxes: x tiles of 3 boxes that overlap by one vector per seam side, the
+  // row cut into as few equal segments as fit (1024 floats: 3 tiles storing 344 + 340 + 340)
+  int ntx = 1, seg = nx;
+  if (variant < 0) {
+    if (!o.star7_pair_xtile) { *why = "rows wider than the fused kernel's tile (star7_pair_xtile=0)"; return nullptr; }
+    variant = o.star7_pair_variant >= 0 && o.star7_pair_variant < kNumPairVariants ? o.star7_pair_variant
+                                                                                   : kPairWideVariant;
+    const int w = kPairVariants[variant].nbx * txb;
+    for (ntx = 2; ntx <= kPairMaxXTiles; ++ntx) {
+      seg = CeilDiv(CeilDiv(nx, ntx), vec) * vec;
+      if (seg + 2 * vec <= w) break;
+    }
+    if (ntx > kPairMaxXTiles) { *why = "rows wider than 16 x tiles of the fused kernel"; return nullptr; }
+  }
   if (nz < 2 || ny < 2) { *why = "grid too thin"; return nullptr; }
   const PairVariant &v = kPairVariants[variant];
 
@@ -549,15 +599,38 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
     long best_cost = -1;
     for (int nzc = 1; nzc <= std::max(1, nz / 4); ++nzc) {
       const int c = CeilDiv(nz, nzc);
-      const long waves = CeilDiv((long)nty * CeilDiv(nz, c), slots);
+      const long waves = CeilDiv((long)nty * ntx * CeilDiv(nz, c), slots);
       const long cost = waves * (c + 3);
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; zc = c; }
     }
   }
   zc = std::max(1, std::min(zc, nz));
-  const int nzc = CeilDiv(nz, zc);
-  const int nitems = nty * nzc;
+  int nzc = CeilDiv(nz, zc);
+  int nitems = nty * ntx * nzc;
   p->grid = std::min(nitems, slots);
+  // Multi-GPU: when whole groups of tiles fit the CTA slots, run the slab's two ends as short
+  // chunks of their own in the first wave, so that the pass number is published a fraction of a
+  // pass after the launch and the neighbours' next pass never waits (with equal chunks filling
+  // one wave exactly, the "boundary" chunks finish with everything else and nothing overlaps)
+  int zbl = 0, nlong = 0, clong = 0, cshort = 0;
+  if (multi && o.early_signal && o.star7_pair_zc <= 0 && o.star7_pair_zbl >= 2) {
+    const int tiles = nty * ntx;
+    const int groups = slots / tiles;
+    if (groups >= 2 && tiles * groups * 10 >= slots * 9) {
+      const int b = o.star7_pair_zbl;
+      // a boundary CTA marches (b + 3) + (cs + 3) planes, an interior one cl + 3: make them equal
+      const int cs = (nz - 2 * b - (groups - 2) * (b + 3)) / groups;
+      if (cs >= 4) {
+        zbl = b;
+        nlong = groups - 2;
+        clong = cs + b + 3;
+        cshort = CeilDiv(nz - 2 * b - nlong * clong, 2);
+        nzc = groups + 2;
+        nitems = tiles * nzc;
+        p->grid = tiles * groups;
+      }
+    }
+  }
 
   Grid *gin[2] = {ga, gb};
   Grid *gout[2] = {gb, ga};
@@ -584,7 +657,12 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
       a->sync = sync;
       // every chunk that reads a halo plane or computes one of the two planes per side the
       // neighbours receive finishes before the pass number is published
-      if (multi) SlabSyncSetBoundary(&a->sync, o.early_signal != 0, nz, zc, nzc, nty, 2);
+      if (multi) SlabSyncSetBoundary(&a->sync, o.early_signal != 0, nz, zc, nzc, nty * ntx, 2);
+      if (zbl > 0) {
+        a->sync.boundary_items = 2 * nty * ntx;  // chunk sequence 0 and 1
+        a->sync.nb_lo = a->sync.nb_hi = 0;
+      }
+      a->zbl = zbl; a->nlong = nlong; a->clong = clong; a->cshort = cshort;
       if (multi) {
         const Grid *go = gout[dir];
         const MemberLayout &ml = go->members[0];
@@ -603,6 +681,13 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
       a->cs = (ET)d0.scalars[3]; a->ct = (ET)d0.scalars[4]; a->cb = (ET)d0.scalars[5];
       a->cc = (ET)d0.scalars[6];
       a->nty = nty; a->nzc = nzc; a->zc = zc; a->nitems = nitems;
+      a->ntx = ntx;
+      for (int t = 0; t < ntx; ++t) {
+        a->txs[t] = std::min(t * seg, nx);
+        a->txe[t] = std::min((t + 1) * seg, nx);
+        // the tile loads one vector beyond its own columns on either side, inside the grid
+        a->tx0[t] = ntx == 1 ? 0 : std::max(0, std::min(a->txs[t] - vec, nx - v.nbx * txb));
+      }
       a->st_hint = o.star7_sthint;
     };
     if (dbl) fill(&p->ad[dir]); else fill(&p->af[dir]);

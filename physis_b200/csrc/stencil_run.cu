@@ -7,6 +7,7 @@
 #include "runtime.h"
 
 #include <algorithm>
+#include <map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -32,6 +33,13 @@ void DestroyHimeno(HimenoPlan *p);
 bool HimenoPushes(const HimenoPlan *p);
 bool HimenoSyncs(const HimenoPlan *p);
 int HimenoPartialCount(const HimenoPlan *p);
+
+struct HimenoPairPlan;
+HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
+                                  const __PSB200StencilDesc &d1, std::string *why);
+bool HimenoPairFacesEqual(Runtime *rt, HimenoPairPlan *p);
+void LaunchHimenoPair(Runtime *rt, HimenoPairPlan *p, int dir);
+void DestroyHimenoPair(HimenoPairPlan *p);
 
 struct PstagPlan;
 PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *why);
@@ -60,7 +68,116 @@ struct SweepPlan {
   __PSDomain gdom;
   std::vector<Grid *> outputs;
   Grid *sum_grid = nullptr;
+  bool cached = false;         // owned by the plan cache, not by the run that prepared it
 };
+
+// ---- plan cache ---------------------------------------------------------------------------
+// The reference's generated run function builds its launch configuration once per call
+// (translator/cuda_runtime_builder.cc:1465-1510) and that costs nothing; here a plan holds
+// encoded TMA descriptors, kernel attributes and an occupancy query, which a program calling
+// `PSStencilRun(..., 1)` in a loop would pay per sweep.  Plans of the hand-written families are
+// therefore kept, keyed by everything they were derived from (family, domain, the grids'
+// identities, members, scalars), until a grid is freed or an option changes.  Generic sweeps
+// are not kept: their plan is two pointers, and the stencil struct they point to is the caller's.
+namespace {
+
+struct PlanCache {
+  std::map<std::string, SweepPlan *> sweeps;
+  std::map<std::string, Star7PairPlan *> pairs;
+  std::map<std::string, HimenoPairPlan *> himeno_pairs;
+  uint64_t hits = 0, misses = 0;
+};
+PlanCache g_plans;
+
+template <typename T>
+void KeyAdd(std::string *k, const T &v) { k->append(reinterpret_cast<const char *>(&v), sizeof(T)); }
+
+std::string DescKey(const __PSB200StencilDesc &d) {
+  std::string k;
+  KeyAdd(&k, d.kind);
+  KeyAdd(&k, d.elm_type);
+  KeyAdd(&k, d.dom);
+  KeyAdd(&k, d.num_grids);
+  for (int i = 0; i < d.num_grids; ++i) {
+    KeyAdd(&k, d.grids[i]);
+    KeyAdd(&k, Grid::FromHandle(d.grids[i])->id);  // ids are never reused, addresses are
+    KeyAdd(&k, d.members[i]);
+  }
+  KeyAdd(&k, d.num_scalars);
+  for (int i = 0; i < d.num_scalars; ++i) KeyAdd(&k, d.scalars[i]);
+  KeyAdd(&k, d.written_mask);
+  KeyAdd(&k, d.z_reach);
+  return k;
+}
+
+}  // namespace
+
+void ClearPlanCache() {
+  for (auto &kv : g_plans.sweeps) {
+    kv.second->cached = false;
+    DestroySweep(kv.second);
+  }
+  g_plans.sweeps.clear();
+  for (auto &kv : g_plans.pairs)
+    if (kv.second) DestroyStar7Pair(kv.second);
+  g_plans.pairs.clear();
+  for (auto &kv : g_plans.himeno_pairs)
+    if (kv.second) DestroyHimenoPair(kv.second);
+  g_plans.himeno_pairs.clear();
+}
+
+static SweepPlan *GetSweepPlan(Runtime *rt, const __PSB200StencilDesc &d) {
+  if (d.kind == PSB200_KIND_GENERIC || !rt->opt.plan_cache) return PrepareSweep(rt, d);
+  const std::string key = DescKey(d);
+  auto it = g_plans.sweeps.find(key);
+  if (it != g_plans.sweeps.end()) {
+    ++g_plans.hits;
+    rt->stats.plan_cache_hits++;
+    return it->second;
+  }
+  ++g_plans.misses;
+  SweepPlan *p = PrepareSweep(rt, d);
+  if (p->kind != PSB200_KIND_GENERIC) {  // a family kernel took it (not the generic fallback)
+    p->cached = true;
+    g_plans.sweeps[key] = p;
+  }
+  return p;
+}
+
+// nullptr when the pair cannot be fused (a decision that is cached too)
+static Star7PairPlan *GetPairPlan(Runtime *rt, const __PSB200StencilDesc &d0,
+                                  const __PSB200StencilDesc &d1, bool *owned) {
+  std::string why;
+  *owned = true;
+  if (!rt->opt.plan_cache) return PrepareStar7Pair(rt, d0, d1, &why);
+  const std::string key = DescKey(d0) + DescKey(d1);
+  auto it = g_plans.pairs.find(key);
+  if (it == g_plans.pairs.end()) {
+    ++g_plans.misses;
+    it = g_plans.pairs.emplace(key, PrepareStar7Pair(rt, d0, d1, &why)).first;
+  } else {
+    ++g_plans.hits;
+  }
+  *owned = false;
+  return it->second;
+}
+
+static HimenoPairPlan *GetHimenoPairPlan(Runtime *rt, const __PSB200StencilDesc &d0,
+                                         const __PSB200StencilDesc &d1, bool *owned) {
+  std::string why;
+  *owned = true;
+  if (!rt->opt.plan_cache) return PrepareHimenoPair(rt, d0, d1, &why);
+  const std::string key = DescKey(d0) + DescKey(d1);
+  auto it = g_plans.himeno_pairs.find(key);
+  if (it == g_plans.himeno_pairs.end()) {
+    ++g_plans.misses;
+    it = g_plans.himeno_pairs.emplace(key, PrepareHimenoPair(rt, d0, d1, &why)).first;
+  } else {
+    ++g_plans.hits;
+  }
+  *owned = false;
+  return it->second;
+}
 
 // Clips the z-range of a domain to this rank's slab.  Specialised kernels work on
 // the local allocation (local plane indices); generic kernels index through the
@@ -260,6 +377,7 @@ void LaunchSweep(Runtime *rt, SweepPlan *p) {
 }
 
 void DestroySweep(SweepPlan *p) {
+  if (p->cached) return;  // the plan cache owns it
   if (p->star7) DestroyStar7(p->star7);
   if (p->himeno) DestroyHimeno(p->himeno);
   if (p->pstag) DestroyPstag(p->pstag);
@@ -281,13 +399,19 @@ extern "C" int __PSB200FusedPassCount(int iter) { return iter >= 3 ? ((iter - 1)
 
 extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200StencilDesc *descs) {
   Runtime *rt = Runtime::Get();
-  // every rank has finished its earlier (synchronous) runtime calls on the grids
-  if (rt->world() > 1) rt->comm->Barrier();
+  // every rank has finished its earlier synchronous runtime calls that wrote grids from the
+  // host (copyin, PSGridSet, free): a neighbour's sweep must not deliver halo planes into a grid
+  // that is still being filled.  Between runs with nothing of the kind in between, the sweeps
+  // order themselves on the device, and the host stays out of it.
+  if (rt->world() > 1 && rt->group_dirty) {
+    rt->comm->Barrier();
+    rt->group_dirty = false;
+  }
   std::vector<SweepPlan *> plans;
   plans.reserve(num_stencils);
   std::string names;
   for (int s = 0; s < num_stencils; ++s) {
-    plans.push_back(PrepareSweep(rt, descs[s]));
+    plans.push_back(GetSweepPlan(rt, descs[s]));
     if (s) names += ", ";
     names += SweepName(plans.back());
   }
@@ -307,9 +431,9 @@ extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200St
   // sweep-by-sweep schedule leaves it.
   int first_unfused = 0;
   Star7PairPlan *pair = nullptr;
+  bool pair_owned = false;
   if (num_stencils == 2 && __PSB200FusedPassCount(iter) > 0 && plans[0]->star7 && plans[1]->star7) {
-    std::string why;
-    pair = PrepareStar7Pair(rt, descs[0], descs[1], &why);
+    pair = GetPairPlan(rt, descs[0], descs[1], &pair_owned);
     if (pair) {
       first_unfused = __PSB200FusedPassCount(iter);
       const bool multi = rt->world() > 1;
@@ -325,6 +449,27 @@ extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200St
       for (int i = 0; i < first_unfused; ++i) {
         LaunchStar7Pair(rt, pair, i & 1);
         if (multi) ++rt->sweep_epoch;
+        rt->stats.kernel_launches++;
+        rt->stats.fused_pairs++;
+      }
+      if (timed) {
+        PSB_CUDA(cudaEventCreate(&emid));
+        PSB_CUDA(cudaEventRecord(emid, rt->stream));
+      }
+    }
+  }
+  // The same for a ping-pong pair of Himeno sweeps (himeno_pair.cu): a pass takes the boundary
+  // cells of the intermediate field from the grid it reads, so it runs only while the boundary
+  // cells of the two grids are bit-equal (one small comparison kernel per run).
+  HimenoPairPlan *hpair = nullptr;
+  bool hpair_owned = false;
+  if (!pair && num_stencils == 2 && __PSB200FusedPassCount(iter) > 0 && plans[0]->himeno && plans[1]->himeno) {
+    hpair = GetHimenoPairPlan(rt, descs[0], descs[1], &hpair_owned);
+    if (hpair && HimenoPairFacesEqual(rt, hpair)) {
+      first_unfused = __PSB200FusedPassCount(iter);
+      for (int s = 0; s < 2; ++s) Grid::FromHandle(descs[0].grids[s])->NoteEmit(descs[0].dom);
+      for (int i = 0; i < first_unfused; ++i) {
+        LaunchHimenoPair(rt, hpair, i & 1);
         rt->stats.kernel_launches++;
         rt->stats.fused_pairs++;
       }
@@ -356,6 +501,7 @@ extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200St
   }
   if (trace) __PSTraceStencilPost(ms);
   for (auto *p : plans) DestroySweep(p);
-  if (pair) DestroyStar7Pair(pair);
+  if (pair && pair_owned) DestroyStar7Pair(pair);
+  if (hpair && hpair_owned) DestroyHimenoPair(hpair);
   return trace ? ms : 0.0f;
 }

@@ -62,6 +62,10 @@ struct SlabSync {
   // words read by Runtime::CheckDeviceErrors) instead of hanging or killing the context
   unsigned long long timeout_ns;
   uint32_t *err;
+  // halo-exchange profile (option halo_profile=1; role of the reference's DataCopyProfile,
+  // runtime/timing.h:11-18): [0] nanoseconds CTAs spent waiting for the neighbours' flags, summed,
+  // [1] the longest single wait, [2] CTAs that waited, [3] launches.  nullptr: not measured.
+  unsigned long long *prof;
   // Overlap of the exchange with interior compute: work items are ordered so that the z chunks
   // touching the slab's two ends come first (SlabChunkOrder): the first `nb_lo` and the last
   // `nb_hi` chunks -- every chunk that reads a halo plane or computes a plane the neighbours
@@ -147,9 +151,24 @@ static __device__ __noinline__ void SlabWaitFlags(const uint32_t *flags, uint32_
   }
 }
 
-// Called by thread 0 of every CTA before the CTA's first __syncthreads().
+// Called by thread 0 of every CTA before the CTA's first __syncthreads().  Only CTAs that
+// will process a boundary item need the neighbours: an interior item reads and writes nothing but
+// this rank's own interior planes, which stream order already protects.  Items are visited in
+// increasing order and the boundary items come first, so a CTA whose first item is interior never
+// meets one.
 __device__ __forceinline__ void SlabSyncWait(const SlabSync &s) {
   if (!s.flags) return;
+  if (s.boundary_items > 0 && (int)blockIdx.x >= s.boundary_items) return;
+  if (s.prof) {
+    const unsigned long long t0 = GlobalTimerNs();
+    SlabWaitFlags(s.flags, s.wait_epoch, s.timeout_ns, s.err);
+    const unsigned long long dt = GlobalTimerNs() - t0;
+    atomicAdd(s.prof + 0, dt);
+    atomicMax(s.prof + 1, dt);
+    atomicAdd(s.prof + 2, 1ull);
+    if (blockIdx.x == 0) atomicAdd(s.prof + 3, 1ull);
+    return;
+  }
   SlabWaitFlags(s.flags, s.wait_epoch, s.timeout_ns, s.err);
 }
 

@@ -81,7 +81,8 @@ def run_diffusion(lib, field, nx, ny, nz, count, coeffs, entry="run_kernel_physi
 HIMENO_GRIDS = ["P0", "P1", "BND", "WRK1", "A0", "A1", "A2", "A3", "B0", "B1", "B2", "C0", "C1", "C2", "GOSA"]
 
 
-def run_himeno(lib, dims, nn, gosa=False, seed=None, omega=None):
+def run_himeno(lib, dims, nn, gosa=False, seed=None, omega=None, each=False, before_finalize=None,
+               p1_differs=False):
     """himeno_init + optional random coefficient fields + jacobi(nn); returns (p0, p1, gosa)."""
     mi, mj, mk = dims
     ne = mi * mj * mk
@@ -93,15 +94,16 @@ def run_himeno(lib, dims, nn, gosa=False, seed=None, omega=None):
         rng = np.random.default_rng(seed)
         for g in range(14):
             b = rng.random(ne, dtype=np.float32)
-            if g in (0, 1):           # p0 and p1 must start identical (boundary cells persist)
-                if g == 0:
+            if g in (0, 1) and not p1_differs:   # the benchmark starts p0 and p1 identical
+                if g == 0:                        # (boundary cells persist)
                     p_init = b
                 b = p_init
             lib.himeno_set_grid(g, b.ctypes.data)
     if omega is not None:
         lib.himeno_set_omega.argtypes = [C.c_float]
         lib.himeno_set_omega(omega)
-    f = lib.himeno_jacobi_gosa if gosa else lib.himeno_jacobi
+    # each: the original benchmark's structure, a PSReduce after every iteration of the pair
+    f = (lib.himeno_jacobi_gosa_each if each else lib.himeno_jacobi_gosa) if gosa else lib.himeno_jacobi
     f.argtypes = [C.c_int]
     f.restype = C.c_float
     g = f(nn)
@@ -111,6 +113,8 @@ def run_himeno(lib, dims, nn, gosa=False, seed=None, omega=None):
     lib.himeno_get_grid(1, p1.ctypes.data)
     gg = np.zeros(ne, np.float32)
     lib.himeno_get_grid(14, gg.ctypes.data)
+    if before_finalize is not None:
+        before_finalize()
     lib.himeno_finalize()
     return p0, p1, g, gg
 

@@ -47,6 +47,8 @@ def case_pair():
              ((512, 17, 24), 4, np.float32, (), iso64), ((64, 30, 19), 6, np.float64, ("star7_pair_zc=2",), co64),
              ((384, 9, 41), 3, np.float32, ("star7_impl=1",), co64), ((128, 21, 26), 5, np.float64, (), iso64),
              ((256, 12, 35), 4, np.float32, ("star7_pair_zc=6",), iso64),
+             # rows wider than one fused tile: x tiles
+             ((1024, 14, 32), 3, np.float32, (), iso64), ((768, 11, 40), 4, np.float32, ("star7_pair_zc=3",), co64),
              # slabs of 4+ planes on up to 3 ranks (fused), of 3 planes on 4 ranks (sweep by sweep)
              ((128, 18, 13), 3, np.float32, (), co64)]
     for shape, iters, dtype, opts, co64 in cases:
@@ -92,7 +94,12 @@ def case_pair_tail():
     co64 = np.array([0.1234567] * 6 + [0.2592598])
     for shape, iters, opts, reps in [((512, 512, 21 * world), 4, ("star7_pair_zc=5",), 12),
                                      ((256, 64, 9 * world), 5, ("star7_pair_zc=1",), 6),
-                                     ((128, 40, 13 * world), 5, ("star7_pair_zc=4",), 6)]:
+                                     ((128, 40, 13 * world), 5, ("star7_pair_zc=4",), 6),
+                                     # the boundary-first schedule (short end chunks in the first wave,
+                                     # unequal interior chunks): 37 y tiles x 4 groups fill the 148 SMs
+                                     ((128, 512, 33 * world), 4, ("star7_pair_zbl=2",), 3),
+                                     ((64, 512, 61 * world), 5, (), 3),
+                                     ((64, 512, 57 * world + 1), 4, ("star7_pair_zbl=3",), 2)]:
         nx, ny, nz = shape
         api.PSInit(["t"], 3, shape)
         for kv in opts:

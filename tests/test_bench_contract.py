@@ -48,3 +48,8 @@ def test_b200_arm_line():
         assert k in r, k
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # the post-run parity cases against the oracle and the exact-solution checksum
+    assert d["parity_ok"] is True, d["parity"]
+    assert d["e2e"]["checksum_ok"] is True
+    assert len(d["parity"]["bit_exact_cases"]) >= 7 and not any("MISMATCH" in c for c in d["parity"]["bit_exact_cases"])
+    assert d["config1_256"]["iter1_loop"]["plan_cache_hits"] > 0

@@ -57,6 +57,14 @@ def _run_pair(shape, iters, dtype, options=(), coeffs=None):
     ((4, 2, 2), 3, ()),
     ((512, 128, 64), 3, ("star7_impl=1",)),
     ((256, 15, 33), 7, ("star7_impl=1", "star7_pair_zc=8")),
+    # rows wider than one tile: x tiles with one-vector seams (BASELINE config 4's 1024 floats)
+    ((1024, 40, 24), 3, ()),
+    ((1024, 64, 64), 5, ()),
+    ((768, 33, 19), 4, ("star7_pair_zc=5",)),
+    ((1100, 22, 9), 5, ()),
+    ((2048, 21, 11), 3, ("star7_pair_zc=3",)),
+    ((640, 41, 10), 3, ("star7_pair_variant=0",)),
+    ((5000, 6, 5), 3, ()),
 ])
 def test_fused_pair_fp32_matches_oracle(shape, iters, opts):
     f0, fa, fb, launches, pairs = _run_pair(shape, iters, np.float32, opts)
@@ -87,6 +95,8 @@ def test_fused_pair_fp32_matches_c_oracle():
     ((128, 30, 17), 5, ("star7_pair_zc=4",)),
     ((64, 14, 12), 3, ()),
     ((50, 9, 7), 3, ()),
+    ((520, 21, 12), 3, ()),
+    ((1024, 19, 9), 4, ("star7_pair_zc=4",)),
 ])
 def test_fused_pair_fp64_matches_oracle(shape, iters, opts):
     f0, fa, fb, launches, pairs = _run_pair(shape, iters, np.float64, opts)
@@ -98,12 +108,12 @@ def test_fused_pair_fp64_matches_oracle(shape, iters, opts):
 
 
 def test_unfused_schedule_unchanged():
-    # star7_fuse=0 keeps the sweep-by-sweep schedule; rows wider than the fused tile fall back
+    # star7_fuse=0 keeps the sweep-by-sweep schedule; so do wide rows with x tiling switched off
     f0, fa, fb, launches, pairs = _run_pair((256, 20, 12), 4, np.float32, ("star7_fuse=0",))
     assert pairs == 0 and launches == 8
     want = H.diffusion7_numpy(f0, (256, 20, 12), CO.astype(np.float32), 8)
     assert np.array_equal(fa.view(np.uint32), want.view(np.uint32))
-    f0, fa, fb, launches, pairs = _run_pair((1024, 12, 6), 3, np.float32)
+    f0, fa, fb, launches, pairs = _run_pair((1024, 12, 6), 3, np.float32, ("star7_pair_xtile=0",))
     assert pairs == 0 and launches == 6
     want = H.diffusion7_numpy(f0, (1024, 12, 6), CO.astype(np.float32), 6)
     assert np.array_equal(fa.view(np.uint32), want.view(np.uint32))
@@ -118,6 +128,8 @@ def test_unfused_schedule_unchanged():
     ((64, 5, 6), 4, ()),
     ((256, 15, 33), 7, ("star7_impl=1", "star7_pair_zc=8")),
     ((256, 47, 20), 3, ("star7_iso=0",)),
+    ((1024, 31, 20), 3, ()),
+    ((1536, 18, 7), 4, ("star7_pair_zc=2",)),
 ])
 def test_fused_pair_equal_coefficients(shape, iters, opts, dtype):
     if dtype == np.float64:
