@@ -50,6 +50,7 @@ struct HimenoArgs {
   int xbase;
   int ntx, nty, nzc, zc, nitems;
   int stages;
+  int st_hint;  // bit 0: streaming (evict-first) stores of p1, bit 1: of the residual grid
   // z-slab view (multi-GPU): local planes of p1 that are also stored into the ring
   // neighbours' halo planes through the CUDA-IPC mapping; -1 / nullptr on one GPU
   int push_lo_z, push_hi_z;
@@ -86,8 +87,8 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
       tma::mbar_init(&empty[s], NW);
     }
     tma::fence_barrier_init();
-    SlabSyncWait(a.sync);
   }
+  SlabSyncWait(a.sync);
   __syncthreads();
 
   const int tiles_xy = a.ntx * a.nty;
@@ -99,14 +100,13 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       const int zseq = item / tiles_xy;
-      const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
       const int txy = item - zseq * tiles_xy;
       const int ty = txy / a.ntx;
       const int tx = txy - ty * a.ntx;
       const int x0 = a.xbase + tx * G::TXB;
       const int y0 = a.dy0 + ty * TY;
-      const int zb = a.dz0 + zci * a.zc;
-      const int ze = min(zb + a.zc, a.dz1);
+      int zb, ze;
+      SlabChunkRange(a.sync, zseq, a.nzc, a.zc, a.dz0, a.dz1, &zb, &ze);
       // the domain is interior in z (checked on the host): planes zb-1 .. ze exist
       for (int z = zb - 1; z <= ze; ++z) {
         tma::mbar_wait(&empty[stage], phase ^ 1u);
@@ -134,14 +134,13 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
     const int zseq = item / tiles_xy;
-    const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
     const int txy = item - zseq * tiles_xy;
     const int ty = txy / a.ntx;
     const int tx = txy - ty * a.ntx;
     const int x = a.xbase + tx * G::TXB + lane * VEC;
     const int y = a.dy0 + ty * TY + warp;
-    const int zb = a.dz0 + zci * a.zc;
-    const int ze = min(zb + a.zc, a.dz1);
+    int zb, ze;
+    SlabChunkRange(a.sync, zseq, a.nzc, a.zc, a.dz0, a.dz1, &zb, &ze);
     const bool row_ok = (y < a.dy1) && (x < a.nx);
     // per-element store mask
     bool ok[VEC];
@@ -236,8 +235,8 @@ HimenoKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
         float *const push1 = (z == a.push_hi_z) ? a.push_hi : nullptr;
         const size_t gp = (size_t)y * a.nx + x;  // offset inside one plane
         if (all_ok) {
-          *reinterpret_cast<float4 *>(a.p1 + g) = o;
-          if (GOSA) *reinterpret_cast<float4 *>(a.gosa + g) = q;
+          StoreVec(reinterpret_cast<float4 *>(a.p1 + g), o, (a.st_hint & 1) != 0);
+          if (GOSA) StoreVec(reinterpret_cast<float4 *>(a.gosa + g), q, (a.st_hint & 2) != 0);
           if (push0) *reinterpret_cast<float4 *>(push0 + gp) = o;
           if (push1) *reinterpret_cast<float4 *>(push1 + gp) = o;
         } else {
@@ -389,6 +388,7 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
   a.nzc = CeilDiv(nzd, zc);
   a.nitems = a.ntx * a.nty * a.nzc;
   a.stages = stages;
+  a.st_hint = rt->opt.himeno_sthint;
   p->grid = std::min(a.nitems, slots);
   if (gosa) {
     Grid::SumCache &sc = g[14]->sum_cache;
@@ -404,7 +404,9 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
     p->pushes = true;
     if (rt->FillSlabSync(&a.sync)) {
       p->syncs = true;
-      SlabSyncSetBoundary(&a.sync, rt->opt.early_signal != 0, nzd, a.zc, a.nzc, a.ntx * a.nty, 1);
+      SlabSyncPlanEnds(&a.sync, rt->opt.early_signal != 0, nzd, &a.zc, &a.nzc, a.ntx * a.nty, 1, rt->opt.slab_zbl);
+      a.nitems = a.ntx * a.nty * a.nzc;
+      p->grid = std::min(a.nitems, slots);
     }
   }
 

@@ -18,8 +18,8 @@
 // from X, which is on the SM anyway.
 //
 // Structure
-//  * a tile is one box of 128 floats (+ 16-byte x halo, as himeno.cu) x H rows, one row per
-//    warp; a CTA marches it along a z chunk.  First-sweep values ("s1") are computed on all H
+//  * a tile is one box of 128 floats (+ 16-byte x halo, as himeno.cu) x H = 12 rows, one row
+//    per warp; a CTA marches it along a z chunk.  First-sweep values ("s1") are computed on all H
 //    rows and all 128 columns, second-sweep values are stored for the H-2 inner rows and the
 //    tile's own columns: tiles overlap by two rows in y and by one 16-byte vector per seam side
 //    in x, chunks by two planes in z (the redundant work; the re-read rows / columns hit in L2);
@@ -28,9 +28,18 @@
 //    its neighbours' cells in three s1 planes, so a slot is recycled one step later than in the
 //    7-point pair);
 //  * one CTA-wide barrier per plane orders both rings; thread 0 re-arms the p slot behind it;
-//  * the coefficient rows are pulled towards the SM by bulk L2 prefetches a few planes ahead
-//    (no registers held), the first sweep reads them with ordinary loads and the second sweep
-//    one step later again (L1 / L2 hits) with evict-first loads.
+//  * the twelve coefficient vectors a thread loads for the first sweep of plane k+1 stay in its
+//    registers for one step and serve the second sweep of the same plane: 96 registers of
+//    coefficients per thread, which is why a CTA has 12 warps (170 registers each) and not 16.
+//    (A first version re-read them for the second sweep and counted on L2: ncu showed 19.7 GB of
+//    DRAM reads per pass instead of 14.9 -- with 148 CTAs streaming 12 arrays the reuse distance
+//    of one step is ~40 MB, and half of the re-reads missed.)  Bulk L2 prefetches pull the next
+//    plane's coefficient rows towards the SM, and the loads are ordinary (evict-normal) ones so
+//    that the rows two neighbouring tiles share are still in L2 for the second of them (with
+//    evict-first loads DRAM reads were 18.8 GB per pass, with ordinary ones 15.8);
+//  * x neighbours of a thread's vector come from the neighbouring lanes by shuffle, only the
+//    edge lanes read the halo column (4-byte shared-memory loads at a 16-byte lane stride are
+//    four-way bank conflicts).
 #include "runtime.h"
 #include "tma.cuh"
 #include "sweep_common.cuh"
@@ -62,6 +71,64 @@ struct HimenoPairArgs {
 
 __device__ __forceinline__ void PrefetchL2(const void *p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// The update of this thread's four cells from three planes of a ring (pb / pc / pt point at the
+// thread's own vector in the planes below / at / above): vectors of the rows above and below
+// from shared memory, x neighbours from the neighbouring lanes, the halo column for the edge
+// lanes.  Cells with upd[j] false keep `keep`'s value.
+__device__ __forceinline__ float4 Update(const float4 (&cf)[12], float omega, const unsigned char *pb,
+                                         const unsigned char *pc, const unsigned char *pt, const float4 &c_c,
+                                         const float4 &keep, const bool (&upd)[4], int lane) {
+  constexpr int ROWB = Geom<float>::ROW_BYTES;
+  auto vec = [](const unsigned char *row, int dy) {
+    return *reinterpret_cast<const float4 *>(row + dy * ROWB);
+  };
+  // the element west of a vector is the previous lane's last, east the next lane's first
+  auto west = [lane](const float4 &v, const unsigned char *row, int dy) {
+    float w = __shfl_up_sync(0xffffffffu, v.w, 1);
+    if (lane == 0) w = *reinterpret_cast<const float *>(row + dy * ROWB - 4);
+    return w;
+  };
+  auto east = [lane](const float4 &v, const unsigned char *row, int dy) {
+    float e = __shfl_down_sync(0xffffffffu, v.x, 1);
+    if (lane == 31) e = *reinterpret_cast<const float *>(row + dy * ROWB + 16);
+    return e;
+  };
+  const float4 c_n = vec(pc, -1), c_s = vec(pc, 1);
+  const float c_cw = west(c_c, pc, 0), c_ce = east(c_c, pc, 0);
+  const float c_nw = west(c_n, pc, -1), c_ne = east(c_n, pc, -1);
+  const float c_sw = west(c_s, pc, 1), c_se = east(c_s, pc, 1);
+  const float4 b_c = vec(pb, 0), b_n = vec(pb, -1), b_s = vec(pb, 1);
+  const float b_w = west(b_c, pb, 0), b_e = east(b_c, pb, 0);
+  const float4 t_c = vec(pt, 0), t_n = vec(pt, -1), t_s = vec(pt, 1);
+  const float t_w = west(t_c, pt, 0), t_e = east(t_c, pt, 0);
+  float4 o = keep;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float c_xm = (j == 0) ? c_cw : Elem(c_c, j - 1);
+    const float c_xp = (j == 3) ? c_ce : Elem(c_c, j + 1);
+    const float n_xm = (j == 0) ? c_nw : Elem(c_n, j - 1);
+    const float n_xp = (j == 3) ? c_ne : Elem(c_n, j + 1);
+    const float s_xm = (j == 0) ? c_sw : Elem(c_s, j - 1);
+    const float s_xp = (j == 3) ? c_se : Elem(c_s, j + 1);
+    const float b_xm = (j == 0) ? b_w : Elem(b_c, j - 1);
+    const float b_xp = (j == 3) ? b_e : Elem(b_c, j + 1);
+    const float t_xm = (j == 0) ? t_w : Elem(t_c, j - 1);
+    const float t_xp = (j == 3) ? t_e : Elem(t_c, j + 1);
+    float ss;
+    const float v = HimenoJacobi(
+        Elem(cf[0], j), Elem(cf[1], j), Elem(cf[2], j), Elem(cf[3], j), Elem(cf[4], j), Elem(cf[5], j),
+        Elem(cf[6], j), Elem(cf[7], j), Elem(cf[8], j), Elem(cf[9], j), Elem(cf[10], j), Elem(cf[11], j),
+        omega,
+        /*ccc*/ Elem(c_c, j), /*ccp*/ Elem(t_c, j), /*cpc*/ Elem(c_s, j), /*pcc*/ c_xp,
+        /*cpp*/ Elem(t_s, j), /*cmp*/ Elem(t_n, j), /*cpm*/ Elem(b_s, j), /*cmm*/ Elem(b_n, j),
+        /*ppc*/ s_xp, /*pmc*/ n_xp, /*mpc*/ s_xm, /*mmc*/ n_xm,
+        /*pcp*/ t_xp, /*pcm*/ b_xp, /*mcp*/ t_xm, /*mcm*/ b_xm,
+        /*ccm*/ Elem(b_c, j), /*cmc*/ Elem(c_n, j), /*mcc*/ c_xm, &ss);
+    if (upd[j]) SetElem(o, j, v);
+  }
+  return o;
 }
 
 template <int H>
@@ -106,12 +173,6 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   auto vec = [](const unsigned char *row, int dy) {
     return *reinterpret_cast<const float4 *>(row + dy * ROWB);
   };
-  auto west = [](const unsigned char *row, int dy) {
-    return *reinterpret_cast<const float *>(row + dy * ROWB - 4);
-  };
-  auto east = [](const unsigned char *row, int dy) {
-    return *reinterpret_cast<const float *>(row + dy * ROWB + 16);
-  };
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
     const int zci = item / tiles_xy;
@@ -137,7 +198,10 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     }
     const bool st_any = st[0] || st[1] || st[2] || st[3];
     const bool st_all = st[0] && st[1] && st[2] && st[3];
-    const bool ld_row = row_in_grid && !row_bnd && (x < a.nx);  // the row computes first-sweep values
+    // the row computes first-sweep values (warp-uniform: the shuffles inside Update need every
+    // lane); lanes beyond the grid's last column compute on zeros and store nothing
+    const bool ld_row = row_in_grid && !row_bnd;
+    const bool ld_ok = (x < a.nx);
     // offset of this thread's vector inside a plane of the coefficient arrays / of `out`
     const size_t gp = (size_t)y * a.nx + x;
 
@@ -166,6 +230,9 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     tma::mbar_wait(&full[1], (par >> 1) & 1u);
     par ^= 1u << 1;
 
+    float4 hold[12];  // coefficients of plane k (loaded as plane m of the previous step)
+#pragma unroll
+    for (int c = 0; c < 12; ++c) hold[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = kfirst; k < ze; ++k) {
       const int m = k + 1;  // plane whose first-sweep values this step computes
       const int slot_c = (slot_b + 1 == kHpInSlots) ? 0 : slot_b + 1;
@@ -173,24 +240,17 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       const bool plane_upd = (m >= 1) && (m < a.nz - 1);
       const size_t gm = (size_t)m * plane_elems + gp;
       // ---- first sweep: s1(m) from p(m-1), p(m), p(m+1) ---------------------------------
-      float4 q0, q1, q2, q3, q4, q5, q6, q7, q8, q9, q10, q11;
+      float4 q[12];
+#pragma unroll
+      for (int c = 0; c < 12; ++c) q[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       const bool compute1 = ld_row && plane_upd;
       if (compute1) {
-        q0 = __ldg(reinterpret_cast<const float4 *>(a.coef[0] + gm));
-        q1 = __ldg(reinterpret_cast<const float4 *>(a.coef[1] + gm));
-        q2 = __ldg(reinterpret_cast<const float4 *>(a.coef[2] + gm));
-        q3 = __ldg(reinterpret_cast<const float4 *>(a.coef[3] + gm));
-        q4 = __ldg(reinterpret_cast<const float4 *>(a.coef[4] + gm));
-        q5 = __ldg(reinterpret_cast<const float4 *>(a.coef[5] + gm));
-        q6 = __ldg(reinterpret_cast<const float4 *>(a.coef[6] + gm));
-        q7 = __ldg(reinterpret_cast<const float4 *>(a.coef[7] + gm));
-        q8 = __ldg(reinterpret_cast<const float4 *>(a.coef[8] + gm));
-        q9 = __ldg(reinterpret_cast<const float4 *>(a.coef[9] + gm));
-        q10 = __ldg(reinterpret_cast<const float4 *>(a.coef[10] + gm));
-        q11 = __ldg(reinterpret_cast<const float4 *>(a.coef[11] + gm));
+#pragma unroll
+        for (int c = 0; c < 12; ++c)
+          if (ld_ok) q[c] = __ldg(reinterpret_cast<const float4 *>(a.coef[c] + gm));
         // and the row of plane m + pf towards L2
         const int mp = m + a.pf;
-        if (lane < 12 && mp < a.nz - 1 && mp <= ze)
+        if (a.pf > 0 && lane < 12 && mp < a.nz - 1 && mp <= ze)
           PrefetchL2(a.coef[lane] + (size_t)mp * plane_elems + (size_t)y * a.nx + xt0,
                      (uint32_t)min(G::TXB, a.nx - xt0) * 4u);
       }
@@ -202,110 +262,39 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const unsigned char *pt = in_ring + slot_t * STAGE + my_off;
         const float4 c_c = vec(pc, 0);
         float4 o = c_c;  // cells the sweep does not update keep the input value
-        if (compute1) {
-          const float4 c_n = vec(pc, -1), c_s = vec(pc, 1);
-          const float c_cw = west(pc, 0), c_ce = east(pc, 0);
-          const float c_nw = west(pc, -1), c_ne = east(pc, -1);
-          const float c_sw = west(pc, 1), c_se = east(pc, 1);
-          const float4 b_c = vec(pb, 0), b_n = vec(pb, -1), b_s = vec(pb, 1);
-          const float b_w = west(pb, 0), b_e = east(pb, 0);
-          const float4 t_c = vec(pt, 0), t_n = vec(pt, -1), t_s = vec(pt, 1);
-          const float t_w = west(pt, 0), t_e = east(pt, 0);
-#pragma unroll
-          for (int j = 0; j < VEC; ++j) {
-            const float c_xm = (j == 0) ? c_cw : Elem(c_c, j - 1);
-            const float c_xp = (j == VEC - 1) ? c_ce : Elem(c_c, j + 1);
-            const float n_xm = (j == 0) ? c_nw : Elem(c_n, j - 1);
-            const float n_xp = (j == VEC - 1) ? c_ne : Elem(c_n, j + 1);
-            const float s_xm = (j == 0) ? c_sw : Elem(c_s, j - 1);
-            const float s_xp = (j == VEC - 1) ? c_se : Elem(c_s, j + 1);
-            const float b_xm = (j == 0) ? b_w : Elem(b_c, j - 1);
-            const float b_xp = (j == VEC - 1) ? b_e : Elem(b_c, j + 1);
-            const float t_xm = (j == 0) ? t_w : Elem(t_c, j - 1);
-            const float t_xp = (j == VEC - 1) ? t_e : Elem(t_c, j + 1);
-            float ss;
-            const float v = HimenoJacobi(
-                Elem(q0, j), Elem(q1, j), Elem(q2, j), Elem(q3, j), Elem(q4, j), Elem(q5, j),
-                Elem(q6, j), Elem(q7, j), Elem(q8, j), Elem(q9, j), Elem(q10, j), Elem(q11, j),
-                a.omega,
-                Elem(c_c, j), Elem(t_c, j), Elem(c_s, j), c_xp,
-                Elem(t_s, j), Elem(t_n, j), Elem(b_s, j), Elem(b_n, j),
-                s_xp, n_xp, s_xm, n_xm,
-                t_xp, b_xp, t_xm, b_xm,
-                Elem(b_c, j), Elem(c_n, j), c_xm, &ss);
-            if (upd[j]) SetElem(o, j, v);
-          }
-        }
+        if (compute1) o = Update(q, a.omega, pb, pc, pt, c_c, o, upd, lane);
         *reinterpret_cast<float4 *>(s1_ring + (m & (kHpS1Slots - 1)) * STAGE + my_off) = o;
       }
       __syncthreads();
       if (issuer) {
         // nobody reads p plane k any more: its slot takes plane k + kHpInSlots
-        const int q = k + kHpInSlots;
-        if (q <= klast) {
+        const int qn = k + kHpInSlots;
+        if (qn <= klast) {
           tma::mbar_arrive_expect_tx(&full[slot_b], (uint32_t)((H + 2) * ROWB));
-          tma::load_3d(in_ring + slot_b * STAGE, &tmap, &full[slot_b], xt0 - G::HX, ty * (H - 2) - 1, q);
+          tma::load_3d(in_ring + slot_b * STAGE, &tmap, &full[slot_b], xt0 - G::HX, ty * (H - 2) - 1, qn);
         }
       }
-      // ---- second sweep: out(k) from s1(k-1), s1(k), s1(k+1) ------------------------------
-      if (k >= zb && st_any) {
+      // ---- second sweep: out(k) from s1(k-1), s1(k), s1(k+1), coefficients held since the
+      //      previous step -----------------------------------------------------------------
+      if (k >= zb && st_row) {
         const size_t gk = (size_t)k * plane_elems + gp;
-        const float4 r0 = __ldcs(reinterpret_cast<const float4 *>(a.coef[0] + gk));
-        const float4 r1 = __ldcs(reinterpret_cast<const float4 *>(a.coef[1] + gk));
-        const float4 r2 = __ldcs(reinterpret_cast<const float4 *>(a.coef[2] + gk));
-        const float4 r3 = __ldcs(reinterpret_cast<const float4 *>(a.coef[3] + gk));
-        const float4 r4 = __ldcs(reinterpret_cast<const float4 *>(a.coef[4] + gk));
-        const float4 r5 = __ldcs(reinterpret_cast<const float4 *>(a.coef[5] + gk));
-        const float4 r6 = __ldcs(reinterpret_cast<const float4 *>(a.coef[6] + gk));
-        const float4 r7 = __ldcs(reinterpret_cast<const float4 *>(a.coef[7] + gk));
-        const float4 r8 = __ldcs(reinterpret_cast<const float4 *>(a.coef[8] + gk));
-        const float4 r9 = __ldcs(reinterpret_cast<const float4 *>(a.coef[9] + gk));
-        const float4 r10 = __ldcs(reinterpret_cast<const float4 *>(a.coef[10] + gk));
-        const float4 r11 = __ldcs(reinterpret_cast<const float4 *>(a.coef[11] + gk));
         const unsigned char *pb = s1_ring + ((k - 1) & (kHpS1Slots - 1)) * STAGE + my_off;
         const unsigned char *pc = s1_ring + (k & (kHpS1Slots - 1)) * STAGE + my_off;
         const unsigned char *pt = s1_ring + ((k + 1) & (kHpS1Slots - 1)) * STAGE + my_off;
-        const float4 c_c = vec(pc, 0), c_n = vec(pc, -1), c_s = vec(pc, 1);
-        const float c_cw = west(pc, 0), c_ce = east(pc, 0);
-        const float c_nw = west(pc, -1), c_ne = east(pc, -1);
-        const float c_sw = west(pc, 1), c_se = east(pc, 1);
-        const float4 b_c = vec(pb, 0), b_n = vec(pb, -1), b_s = vec(pb, 1);
-        const float b_w = west(pb, 0), b_e = east(pb, 0);
-        const float4 t_c = vec(pt, 0), t_n = vec(pt, -1), t_s = vec(pt, 1);
-        const float t_w = west(pt, 0), t_e = east(pt, 0);
-        float4 o;
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          const float c_xm = (j == 0) ? c_cw : Elem(c_c, j - 1);
-          const float c_xp = (j == VEC - 1) ? c_ce : Elem(c_c, j + 1);
-          const float n_xm = (j == 0) ? c_nw : Elem(c_n, j - 1);
-          const float n_xp = (j == VEC - 1) ? c_ne : Elem(c_n, j + 1);
-          const float s_xm = (j == 0) ? c_sw : Elem(c_s, j - 1);
-          const float s_xp = (j == VEC - 1) ? c_se : Elem(c_s, j + 1);
-          const float b_xm = (j == 0) ? b_w : Elem(b_c, j - 1);
-          const float b_xp = (j == VEC - 1) ? b_e : Elem(b_c, j + 1);
-          const float t_xm = (j == 0) ? t_w : Elem(t_c, j - 1);
-          const float t_xp = (j == VEC - 1) ? t_e : Elem(t_c, j + 1);
-          float ss;
-          const float v = HimenoJacobi(
-              Elem(r0, j), Elem(r1, j), Elem(r2, j), Elem(r3, j), Elem(r4, j), Elem(r5, j),
-              Elem(r6, j), Elem(r7, j), Elem(r8, j), Elem(r9, j), Elem(r10, j), Elem(r11, j),
-              a.omega,
-              Elem(c_c, j), Elem(t_c, j), Elem(c_s, j), c_xp,
-              Elem(t_s, j), Elem(t_n, j), Elem(b_s, j), Elem(b_n, j),
-              s_xp, n_xp, s_xm, n_xm,
-              t_xp, b_xp, t_xm, b_xm,
-              Elem(b_c, j), Elem(c_n, j), c_xm, &ss);
-          SetElem(o, j, v);
-        }
+        const float4 c_c = vec(pc, 0);
+        const bool all4[VEC] = {true, true, true, true};
+        const float4 o = Update(hold, a.omega, pb, pc, pt, c_c, c_c, all4, lane);
         if (st_all) {
           __stcs(reinterpret_cast<float4 *>(a.out + gk), o);
-        } else {
+        } else if (st_any) {
 #pragma unroll
           for (int j = 0; j < VEC; ++j)
             if (st[j]) a.out[gk + j] = Elem(o, j);
         }
       }
+      // plane m's coefficients serve the second sweep of the next step
+#pragma unroll
+      for (int c = 0; c < 12; ++c) hold[c] = q[c];
       slot_b = slot_c;
     }
   }
@@ -393,7 +382,7 @@ HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
         *why = "both sweeps must cover exactly the interior"; return nullptr;
       }
   }
-  constexpr int H = 16;
+  constexpr int H = 12;
   HimenoPairPlan *p = new HimenoPairPlan();
   p->fn = (const void *)HimenoPairKernel<H>;
   p->smem = HpGeom<H>::SMEM;
@@ -401,8 +390,7 @@ HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
   p->g[0] = g[0];
   p->g[1] = g[1];
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-  // shared memory: just the rings; the rest of the SM's array stays L1, which is where the
-  // second sweep finds the coefficient rows the first sweep read one step earlier
+  // shared memory: just the rings
   {
     const int pct = (int)(((p->smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
     PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(pct, 100)));
@@ -461,7 +449,7 @@ HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
     }
     a.dz0 = 1;
     a.dz1 = nz - 1;
-    a.pf = std::max(1, std::min(o.himeno_pair_pf, 8));
+    a.pf = std::max(0, std::min(o.himeno_pair_pf, 8));
   }
   p->grid = std::min(p->args[0].nitems, slots);
   return p;

@@ -115,8 +115,8 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
       tma::mbar_init(&empty[s], NW);
     }
     tma::fence_barrier_init();
-    SlabSyncWait(a.sync);
   }
+  SlabSyncWait(a.sync);
   __syncthreads();
 
   const int tiles_xy = a.ntx * a.nty;
@@ -131,14 +131,13 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
     uint32_t epar = 0;  // bit s: parity of the next "slot s is free" phase to wait for
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       const int zseq = item / tiles_xy;
-      const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
       const int txy = item - zseq * tiles_xy;
       const int ty = txy / a.ntx;
       const int tx = txy - ty * a.ntx;
       const int x0 = tx * (NBX * G::TXB);
       const int y0 = a.dy0 + ty * TY;
-      const int zb = a.dz0 + zci * a.zc;
-      const int ze = min(zb + a.zc, a.dz1);
+      int zb, ze;
+      SlabChunkRange(a.sync, zseq, a.nzc, a.zc, a.dz0, a.dz1, &zb, &ze);
       const int yn = (y0 - 1 + a.ny) % a.ny;   // periodic halo rows
       const int ys = (y0 + TY) % a.ny;
       uint32_t tx_bytes = 0;
@@ -210,16 +209,28 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
   // this thread's 3 x (RY+1) vertices of kap plane KZ, which arrived in ring slot SLOT: patch
   // row q has flat row number R = KZ*ky + ytile + q; the rows with even R are in the first
   // box, those with odd R in the second (whose first wanted column is `kodd` elements in),
-  // and in either box row q is row q/2
+  // and in either box row q is row q/2.  A thread wants the three vertices x, x+1, x+2 of a row,
+  // its lane neighbour x+2, x+3, x+4: one conflict-free 16-byte load per thread fetches a
+  // pair, the rest comes from the next lane by shuffle (8-byte loads at this 16-byte lane
+  // stride are two-way bank conflicts: ncu counted 20 M of them per sweep); lane 31 loads the
+  // pair after its own instead.  Which pair a thread loads depends on the row's parity
+  // (warp-uniform): the wanted vertices start at the pair's first or second element.
 #define PS_LOAD_KAP(K, SLOT, KZ) do { \
     const unsigned char *kp__ = my_kap + (SLOT) * STAGE_BYTES; \
     const int p0__ = ((KZ) * a.ky + ytile) & 1; \
     _Pragma("unroll") for (int r = 0; r <= RY; ++r) { \
       const int q__ = row0 + r; \
       const int odd__ = (p0__ + q__) & 1; \
-      const double *src__ = reinterpret_cast<const double *>( \
-          kp__ + odd__ * (L::KAP_ODD - L::KAP) + (q__ >> 1) * KROW) + odd__ * kodd; \
-      K[r][0] = src__[0]; K[r][1] = src__[1]; K[r][2] = src__[2]; \
+      const unsigned char *row__ = kp__ + odd__ * (L::KAP_ODD - L::KAP) + (q__ >> 1) * KROW; \
+      const double2 v__ = *reinterpret_cast<const double2 *>(row__); \
+      double nx__ = __shfl_down_sync(0xffffffffu, v__.x, 1); \
+      double ny__ = __shfl_down_sync(0xffffffffu, v__.y, 1); \
+      if (lane_last) { \
+        const double2 w__ = *reinterpret_cast<const double2 *>(row__ + 16); \
+        nx__ = w__.x; ny__ = w__.y; \
+      } \
+      if (odd__ * kodd) { K[r][0] = v__.y; K[r][1] = nx__; K[r][2] = ny__; } \
+      else { K[r][0] = v__.x; K[r][1] = v__.y; K[r][2] = nx__; } \
     } \
   } while (0)
   // One plane z: the centre plane is in registers (CEN) and in slot CS, the top plane arrives
@@ -280,15 +291,14 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
     const int zseq = item / tiles_xy;
-    const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
     const int txy = item - zseq * tiles_xy;
     const int ty = txy / a.ntx;
     const int tx = txy - ty * a.ntx;
     const int bx0 = tx * (NBX * G::TXB) + bx * G::TXB;
     const int x = bx0 + lane * VEC;
     const int ybase = a.dy0 + ty * TY + wy * RY;
-    const int zb = a.dz0 + zci * a.zc;
-    const int ze = min(zb + a.zc, a.dz1);
+    int zb, ze;
+    SlabChunkRange(a.sync, zseq, a.nzc, a.zc, a.dz0, a.dz1, &zb, &ze);
     const bool x_ok = (x >= a.dx0) && (x + VEC <= a.dx1) && (x < a.nx);
     // x neighbours of lane 0 / lane 31: the box's own x halo, or on the periodic faces the
     // wrap column (16 bytes per row: x = nx-2, nx-1 west of the grid, x = 0, 1 east of it)
@@ -490,14 +500,25 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   }
   a.push_lo_z = a.push_hi_z = -1;
   a.sync = SlabSync{};
-  if (SlabPushTargets(rt, *u, wr, (void **)&a.push_lo, (void **)&a.push_hi, sizeof(double))) {
+  // The exchange of this sweep is copy-based by default (peer copies of the two boundary planes
+  // and stream-ordered flags after the kernel): measured on 2 GPUs at 512^3 per GPU it costs 7 %
+  // of a sweep against 13-15 % for the in-kernel form (option pstag_push=1) -- with 1024 small
+  // tiles per slab every work item carries a fence and a counter update, and short boundary
+  // chunks that would confine them pay the ring's fill latency 2048 times.
+  if (rt->opt.pstag_push &&
+      SlabPushTargets(rt, *u, wr, (void **)&a.push_lo, (void **)&a.push_hi, sizeof(double))) {
     a.push_lo_z = u->halo;
     a.push_hi_z = u->halo + u->nz_loc - 1;
     p->pushes = true;
     if (rt->FillSlabSync(&a.sync)) {
       p->syncs = true;
-      SlabSyncSetBoundary(&a.sync, rt->opt.early_signal != 0, nzd, a.zc, a.nzc, a.ntx * a.nty, 1);
+      SlabSyncPlanEnds(&a.sync, rt->opt.early_signal != 0, nzd, &a.zc, &a.nzc, a.ntx * a.nty, 1, rt->opt.slab_zbl);
+      a.nitems = tiles * a.nzc;
+      p->grid = std::min(a.nitems, slots);
     }
+    // timing experiments only (results are wrong): what the exchange costs the kernel
+    if (rt->opt.debug_slab & 1) a.push_lo_z = a.push_hi_z = -1;
+    if (rt->opt.debug_slab & 2) { a.sync.flags = nullptr; a.sync.done = nullptr; a.sync.boundary_items = 0; }
   }
 
   int dimv[3] = {nx, ny, nz};

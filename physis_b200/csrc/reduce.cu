@@ -171,8 +171,9 @@ void Run(Runtime *rt, const Grid &g, void *out_host) {
   bool from_partials = false;
   if constexpr (std::is_same<T, float>::value && OP == PS_SUM) {
     if (g.sum_cache.valid && rt->opt.reduce_fuse) {
-      FoldPartials<<<1, kThreads, 0, rt->stream>>>((const double *)g.sum_cache.partials->get(),
-                                                  g.sum_cache.count, result);
+      // (a rank without a share of the sweep's domain holds no partials: count 0, sum 0)
+      const double *part = g.sum_cache.partials ? (const double *)g.sum_cache.partials->get() : nullptr;
+      FoldPartials<<<1, kThreads, 0, rt->stream>>>(part, part ? g.sum_cache.count : 0, result);
       rt->stats.kernel_launches += 1;
       rt->stats.reduces_from_partials += 1;
       from_partials = true;

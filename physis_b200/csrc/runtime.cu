@@ -449,20 +449,17 @@ static int ParseKV(Options *o, const std::string &kv) {
   if (eq == std::string::npos) return -1;
   std::string k = kv.substr(0, eq);
   long val = atol(kv.c_str() + eq + 1);
-  if (k == "star7_ty") o->star7_ty = (int)val;
-  else if (k == "star7_ry") o->star7_ry = (int)val;
-  else if (k == "star7_nbx") o->star7_nbx = (int)val;
-  else if (k == "star7_stages") o->star7_stages = (int)val;
+  if (k == "star7_stages") o->star7_stages = (int)val;
   else if (k == "star7_zc") o->star7_zc = (int)val;
   else if (k == "star7_occ") o->star7_occ = (int)val;
   else if (k == "star7_variant") o->star7_variant = (int)val;
-  else if (k == "star7_l2hint") o->star7_l2hint = (int)val;
   else if (k == "star7_impl") o->star7_impl = (int)val;
   else if (k == "star7_sthint") o->star7_sthint = (int)val;
   else if (k == "star7_fuse") o->star7_fuse = (int)val;
   else if (k == "star7_pair_zc") o->star7_pair_zc = (int)val;
   else if (k == "star7_pair_xtile") o->star7_pair_xtile = (int)val;
   else if (k == "star7_pair_zbl") o->star7_pair_zbl = (int)val;
+  else if (k == "star7_pair_zbias") o->star7_pair_zbias = (int)val;
   else if (k == "star7_pair_variant") o->star7_pair_variant = (int)val;
   else if (k == "star7_iso") o->star7_iso = (int)val;
   else if (k == "himeno_by") o->himeno_by = (int)val;
@@ -471,11 +468,13 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "himeno_occ") o->himeno_occ = (int)val;
   else if (k == "himeno_carveout") o->himeno_carveout = (int)val;
   else if (k == "himeno_fuse") o->himeno_fuse = (int)val;
+  else if (k == "himeno_sthint") o->himeno_sthint = (int)val;
   else if (k == "himeno_pair_zc") o->himeno_pair_zc = (int)val;
   else if (k == "himeno_pair_pf") o->himeno_pair_pf = (int)val;
   else if (k == "pstag_variant") o->pstag_variant = (int)val;
   else if (k == "pstag_stages") o->pstag_stages = (int)val;
   else if (k == "pstag_occ") o->pstag_occ = (int)val;
+  else if (k == "pstag_push") o->pstag_push = (int)val;
   else if (k == "time_kernels") o->time_kernels = (int)val;
   else if (k == "halo") o->halo = (int)val;
   else if (k == "halo_push") o->halo_push = (int)val;
@@ -484,10 +483,12 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "stage_chunk_mb") o->stage_chunk = (size_t)val << 20;
   else if (k == "copy_threads") o->copy_threads = (int)val;
   else if (k == "early_signal") o->early_signal = (int)val;
+  else if (k == "slab_zbl") o->slab_zbl = (int)val;
   else if (k == "sync_timeout_s") o->sync_timeout_s = (int)val;
   else if (k == "reduce_fuse") o->reduce_fuse = (int)val;
   else if (k == "plan_cache") o->plan_cache = (int)val;
   else if (k == "halo_profile") o->halo_profile = (int)val;
+  else if (k == "debug_slab") o->debug_slab = (int)val;
   else return -1;
   return 0;
 }

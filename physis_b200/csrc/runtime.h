@@ -163,19 +163,23 @@ class GridSpace {
 };
 
 struct Options {
-  // star-7 sweep tile shape (see star7.cu); 0 = automatic
-  int star7_ty = 0, star7_ry = 0, star7_nbx = 0, star7_stages = 0, star7_zc = 0, star7_occ = 0;
-  int star7_variant = -1 /* auto */, star7_l2hint = 0, star7_sthint = 0, star7_impl = 2;
+  // star-7 sweep: tile shape (index into star7.cu's table, -1 = automatic), ring depth, z chunk,
+  // resident CTAs (0 = automatic), streaming stores, arithmetic form (1 scalar / 2 packed adds)
+  int star7_stages = 0, star7_zc = 0, star7_occ = 0;
+  int star7_variant = -1, star7_sthint = 0, star7_impl = 2;
   int star7_fuse = 1;     // 1: a ping-pong pair of whole-grid 7-pt sweeps runs as one fused two-sweep pass
   int star7_pair_zc = 0;  // z chunk of the fused kernel; 0 = automatic
   int star7_pair_zbl = 8;       // multi-GPU: planes of the boundary chunks that run first (0: equal chunks)
+  int star7_pair_zbias = 8;     // ... and planes by which their CTAs' interior chunks are shorter
   int star7_pair_xtile = 1;     // 1: rows wider than one fused tile are cut into x tiles
   int star7_pair_variant = -1;  // tile shape of the x-tiled form; -1 = automatic
   int star7_iso = 1;      // 1: equal neighbour coefficients use the shared-product form of the fused kernel
   int himeno_by = 0, himeno_zc = 0, himeno_stages = 0, himeno_occ = 0, himeno_carveout = 0;
+  int himeno_sthint = 0;    // bit 0 / bit 1: evict-first stores of p1 / of the residual grid
   int himeno_fuse = 1;      // 1: a ping-pong pair of interior Himeno sweeps runs as fused two-sweep passes
   int himeno_pair_zc = 0;   // z chunk of the fused Himeno kernel; 0 = automatic
-  int himeno_pair_pf = 2;   // planes ahead the coefficient rows are prefetched into L2
+  int himeno_pair_pf = 1;   // planes ahead the coefficient rows are prefetched into L2
+  int pstag_push = 0;     // 1: the config-5 sweep stores its halo planes and orders itself in the kernel
   int pstag_variant = 13 /* measured best, profiles/r1_tune_pstag_512.csv */, pstag_stages = 0, pstag_occ = 0;
   int time_kernels = 0;        // per-family CUDA-event timing (for bench roofline)
   size_t stage_chunk = 64u << 20;  // pinned staging chunk for pageable copies
@@ -188,11 +192,13 @@ struct Options {
                          //    the neighbour's halo (fused); 0: peer copies after the kernel
   int sync_mode = 2;     // 2: waits and signals fused into the sweep kernels, 0: stream
                          //    memory operations, 1: one-thread signal/wait kernels
+  int slab_zbl = 8;      // single sweeps on z-slabs: planes of the boundary chunks that run first (0: equal chunks)
   int early_signal = 1;  // with sync_mode 2: publish a sweep's number as soon as its boundary z chunks
                          // are done, so that the neighbours' next sweep overlaps the interior chunks
   int copyout_gather = 1;  // PSGridCopyout fills the whole host array on every rank
   int sync_timeout_s = 120;  // a neighbour silent for longer than this is a reported error
   int plan_cache = 1;    // keep prepared sweep plans across PSStencilRun calls
+  int debug_slab = 0;    // timing experiments (WRONG results): bit 0 no halo stores, bit 1 no neighbour ordering
   int halo_profile = 0;  // 1: sweeps record how long their CTAs wait for the ring neighbours
   int reduce_fuse = 1;   // PSReduce(PS_SUM) folds the partial sums the producing sweep left (himeno.cu)
 };

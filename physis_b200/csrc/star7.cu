@@ -48,7 +48,6 @@ struct Star7Args {
   int ntx, nty, nzc, zc;             // tiles in x, y; number and length of z chunks
   int nitems;
   int stages;
-  int l2_hint;   // 1: loads carry an evict_first policy
   int st_hint;   // 1: streaming (evict-first) stores
   // z-slab view (multi-GPU; on one GPU zcl = {0, nz-1} and nothing is pushed):
   // local planes at which the bottom / top neighbour is clamped to the centre,
@@ -57,215 +56,21 @@ struct Star7Args {
   // mapping, into the ring neighbour's halo plane (fused halo exchange over NVLink)
   int push_lo_z, push_hi_z;
   T *push_lo, *push_hi;
-  SlabSync sync;  // neighbour ordering fused into the kernel (second form only)
+  SlabSync sync;  // neighbour ordering fused into the kernel
 };
 
-// TY  rows of the CTA tile, RY rows per thread, NBX boxes side by side in x,
-// MINB resident CTAs per SM the register budget is sized for.
-template <typename T, int TY, int RY, int NBX, int MINB>
-__global__ void __launch_bounds__((NBX * (TY / RY) + 1) * 32, MINB)
-Star7Kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Star7Args<T> a) {
-  using G = Geom<T>;
-  using V = typename VecOf<T>::type;
-  constexpr int VEC = G::VEC;
-  constexpr int NWY = TY / RY;
-  constexpr int NW = NBX * NWY;  // consumer warps
-  constexpr int ROWB = G::ROW_BYTES;
-  constexpr int BOX_STRIDE = BoxStride<T, TY>();
-  constexpr int STAGE_BYTES = NBX * BOX_STRIDE;
-  static_assert(TY % RY == 0, "TY must be a multiple of RY");
-
-  extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem);
-  uint64_t *empty = full + kMaxStages;
-  unsigned char *planes = smem + kBarrierBytes;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int S = a.stages;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      tma::mbar_init(&full[s], 1);
-      tma::mbar_init(&empty[s], NW);
-    }
-    tma::fence_barrier_init();
-  }
-  __syncthreads();
-
-  const int tiles_xy = a.ntx * a.nty;
-
-  if (warp == NW) {
-    // ------------------------------------------------------------ producer
-    if (lane != 0) return;
-    tma::prefetch_tensormap(&tmap);
-    const uint64_t policy = tma::policy_evict_first();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-      const int zci = item / tiles_xy;
-      const int txy = item - zci * tiles_xy;
-      const int ty = txy / a.ntx;
-      const int tx = txy - ty * a.ntx;
-      const int x0 = a.xbase + tx * (NBX * G::TXB);
-      const int y0 = a.dy0 + ty * TY;
-      const int zb = a.dz0 + zci * a.zc;
-      const int ze = min(zb + a.zc, a.dz1);
-      const int zfirst = zb > 0 ? zb - 1 : zb;
-      const int zlast = min(ze, a.nz - 1);
-      int nbox = 0;
-#pragma unroll
-      for (int b = 0; b < NBX; ++b) nbox += (x0 + b * G::TXB < a.nx) ? 1 : 0;
-      const uint32_t tx_bytes = (uint32_t)nbox * (uint32_t)((TY + 2) * ROWB);
-      for (int z = zfirst; z <= zlast; ++z) {
-        tma::mbar_wait(&empty[stage], phase ^ 1u);
-        tma::mbar_arrive_expect_tx(&full[stage], tx_bytes);
-        unsigned char *dst = planes + stage * STAGE_BYTES;
-#pragma unroll
-        for (int b = 0; b < NBX; ++b) {
-          const int bx0 = x0 + b * G::TXB;
-          if (bx0 < a.nx) {
-            if (a.l2_hint)
-              tma::load_3d_hint(dst + b * BOX_STRIDE, &tmap, &full[stage], bx0 - G::HX, y0 - 1, z,
-                                policy);
-            else
-              tma::load_3d(dst + b * BOX_STRIDE, &tmap, &full[stage], bx0 - G::HX, y0 - 1, z);
-          }
-        }
-        if (++stage == S) { stage = 0; phase ^= 1u; }
-      }
-    }
-    return;
-  }
-
-  // -------------------------------------------------------------- consumers
-  const int bx = warp % NBX;
-  const int wy = warp / NBX;
-  // byte offset of this thread's vector inside a box row / of its first row
-  const int col_off = (G::HX + lane * VEC) * (int)sizeof(T);
-  const int row0 = wy * RY;  // smem row of the north halo of this thread's rows
-
-  int stage = 0;       // ring position of the next plane to consume
-  uint32_t phase = 0;
-  auto advance = [&]() {
-    if (++stage == S) { stage = 0; phase ^= 1u; }
-  };
-  auto release = [&](int st) {
-    __syncwarp();
-    if (lane == 0) tma::mbar_arrive(&empty[st]);
-  };
-
-  for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-    const int zci = item / tiles_xy;
-    const int txy = item - zci * tiles_xy;
-    const int ty = txy / a.ntx;
-    const int tx = txy - ty * a.ntx;
-    const int x = a.xbase + tx * (NBX * G::TXB) + bx * G::TXB + lane * VEC;
-    const int ybase = a.dy0 + ty * TY + wy * RY;
-    const int zb = a.dz0 + zci * a.zc;
-    const int ze = min(zb + a.zc, a.dz1);
-    const bool x_ok = (x >= a.dx0) && (x + VEC <= a.dx1);
-    const bool x_first = (x == 0);
-    const bool x_last = (x + VEC == a.nx);
-
-    const unsigned char *box = planes + bx * BOX_STRIDE;
-    V cen[RY], bot[RY], top[RY];
-
-    if (zb > 0) {
-      tma::mbar_wait(&full[stage], phase);
-      const unsigned char *p = box + stage * STAGE_BYTES + (row0 + 1) * ROWB + col_off;
-#pragma unroll
-      for (int r = 0; r < RY; ++r) bot[r] = *reinterpret_cast<const V *>(p + r * ROWB);
-      release(stage);
-      advance();
-    }
-    int stage_c = stage;
-    tma::mbar_wait(&full[stage], phase);
-    {
-      const unsigned char *p = box + stage * STAGE_BYTES + (row0 + 1) * ROWB + col_off;
-#pragma unroll
-      for (int r = 0; r < RY; ++r) cen[r] = *reinterpret_cast<const V *>(p + r * ROWB);
-    }
-    advance();
-
-    bool has_top = false;
-    for (int z = zb; z < ze; ++z) {
-      has_top = (z + 1 < a.nz);
-      const int stage_t = stage;
-      if (has_top) {
-        tma::mbar_wait(&full[stage], phase);
-        const unsigned char *p = box + stage * STAGE_BYTES + (row0 + 1) * ROWB + col_off;
-#pragma unroll
-        for (int r = 0; r < RY; ++r) top[r] = *reinterpret_cast<const V *>(p + r * ROWB);
-      }
-      const unsigned char *cb = box + stage_c * STAGE_BYTES;
-      const V north = *reinterpret_cast<const V *>(cb + row0 * ROWB + col_off);
-      const V south = *reinterpret_cast<const V *>(cb + (row0 + RY + 1) * ROWB + col_off);
-      const bool z_first = (z == a.zcl_lo), z_last = (z == a.zcl_hi);
-      T *const push0 = (z == a.push_lo_z) ? a.push_lo : nullptr;
-      T *const push1 = (z == a.push_hi_z) ? a.push_hi : nullptr;
-#pragma unroll
-      for (int r = 0; r < RY; ++r) {
-        const int y = ybase + r;
-        const V c = cen[r];
-        T wv = __shfl_up_sync(0xffffffffu, Elem(c, VEC - 1), 1);
-        T ev = __shfl_down_sync(0xffffffffu, Elem(c, 0), 1);
-        const unsigned char *rowp = cb + (row0 + 1 + r) * ROWB;
-        if (lane == 0) wv = *reinterpret_cast<const T *>(rowp + (G::HX - 1) * sizeof(T));
-        if (lane == 31) ev = *reinterpret_cast<const T *>(rowp + (G::HX + G::TXB) * sizeof(T));
-        V nv = (r == 0) ? north : cen[r - 1];
-        V sv = (r == RY - 1) ? south : cen[r + 1];
-        V bv = bot[r], tv = top[r];
-        if (y == 0) nv = c;
-        if (y == a.ny - 1) sv = c;
-        if (z_first) bv = c;
-        if (z_last) tv = c;
-        V o;
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          const T cj = Elem(c, j);
-          T wj = (j == 0) ? wv : Elem(c, j - 1);
-          T ej = (j == VEC - 1) ? ev : Elem(c, j + 1);
-          if (j == 0 && x_first) wj = cj;
-          if (j == VEC - 1 && x_last) ej = cj;
-          SetElem(o, j, Point7<T>(a, cj, wj, ej, Elem(sv, j), Elem(nv, j), Elem(bv, j), Elem(tv, j)));
-        }
-        if (x_ok && y >= a.dy0 && y < a.dy1) {
-          V *dst = reinterpret_cast<V *>(a.out + ((size_t)z * a.ny + y) * a.nx + x);
-          StoreVec(dst, o, a.st_hint != 0);
-          if (push0) *reinterpret_cast<V *>(push0 + (size_t)y * a.nx + x) = o;
-          if (push1) *reinterpret_cast<V *>(push1 + (size_t)y * a.nx + x) = o;
-        }
-      }
-      release(stage_c);
-      if (has_top) {
-        stage_c = stage_t;
-        advance();
-#pragma unroll
-        for (int r = 0; r < RY; ++r) {
-          bot[r] = cen[r];
-          cen[r] = top[r];
-        }
-      }
-    }
-    if (has_top) release(stage_c);  // plane ze was loaded as `top` only
-  }
-}
-
-
-// ---------------------------------------------------------------- second form
+// The consumers' instruction count is cut to what the stencil needs (a first form of this
+// kernel, since removed, ran at 64 % of issue slots busy with the fp32 work a third of the
+// instructions): clamps are taken out of the per-element path (z: register copies on the one
+// plane that needs them; y: warp-uniform branch; x: one select on the edge lanes), the z window
+// rotates by renaming instead of moving registers, addresses advance by adds, the mbarrier
+// wait is two instructions on its fast path, and -- fp32 only -- the six additions per point
+// run as packed add.rn.f32x2 (SASS FADD2) on pairs of separately rounded scalar products.
+// (ptxas contracts a packed multiply feeding a packed add into FFMA2 even with explicit .rn,
+// which would change the rounding, so the multiplies stay scalar.)
 //
-// Same structure and results as Star7Kernel, with the consumers' instruction
-// count cut to what the stencil needs (ncu of the first form: 64 % of issue
-// slots busy, the fp32 work being a third of the instructions): clamps are taken
-// out of the per-element path (z: register copies on the one plane that needs
-// them; y: warp-uniform branch; x: one select on the edge lanes), the z window
-// rotates by renaming instead of moving registers, addresses advance by adds,
-// the mbarrier wait is two instructions on its fast path, and -- fp32 only --
-// the six additions per point run as packed add.rn.f32x2 (SASS FADD2) on pairs
-// of separately rounded scalar products.  (ptxas contracts a packed multiply
-// feeding a packed add into FFMA2 even with explicit .rn, which would change the
-// rounding, so the multiplies stay scalar.)
+// TY rows of the CTA tile, RY rows per thread, NBX boxes side by side in x, MINB resident CTAs
+// per SM the register budget is sized for; FP: packed adds.
 
 
 // FR ("full row"): the NBX boxes of a tile cover a whole grid row, so boxes carry no
@@ -305,8 +110,8 @@ Star7KernelV2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       tma::mbar_init(&empty[s], NW);
     }
     tma::fence_barrier_init();
-    SlabSyncWait(a.sync);
   }
+  SlabSyncWait(a.sync);
   __syncthreads();
 
   const int tiles_xy = a.ntx * a.nty;
@@ -319,14 +124,13 @@ Star7KernelV2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       const int zseq = item / tiles_xy;
-      const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
       const int txy = item - zseq * tiles_xy;
       const int ty = txy / a.ntx;
       const int tx = txy - ty * a.ntx;
       const int x0 = a.xbase + tx * (NBX * G::TXB);
       const int y0 = a.dy0 + ty * TY;
-      const int zb = a.dz0 + zci * a.zc;
-      const int ze = min(zb + a.zc, a.dz1);
+      int zb, ze;
+      SlabChunkRange(a.sync, zseq, a.nzc, a.zc, a.dz0, a.dz1, &zb, &ze);
       const int zfirst = zb > 0 ? zb - 1 : zb;
       const int zlast = min(ze, a.nz - 1);
       int nbox = 0;
@@ -373,14 +177,13 @@ Star7KernelV2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
     const int zseq = item / tiles_xy;
-    const int zci = SlabChunkOrder(a.sync, zseq, a.nzc);
     const int txy = item - zseq * tiles_xy;
     const int ty = txy / a.ntx;
     const int tx = txy - ty * a.ntx;
     const int x = a.xbase + tx * (NBX * G::TXB) + bx * G::TXB + lane * VEC;
     const int ybase = a.dy0 + ty * TY + wy * RY;
-    const int zb = a.dz0 + zci * a.zc;
-    const int ze = min(zb + a.zc, a.dz1);
+    int zb, ze;
+    SlabChunkRange(a.sync, zseq, a.nzc, a.zc, a.dz0, a.dz1, &zb, &ze);
     const bool x_ok = (x >= a.dx0) && (x + VEC <= a.dx1);
     const bool x_first = (x == 0);
     const bool x_last = (x + VEC == a.nx);
@@ -481,48 +284,29 @@ Star7KernelV2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
 
 struct VariantInfo {
   int ty, ry, nbx;
-  const void *f32;
+  const void *f32[2];  // scalar / packed-add arithmetic
   const void *f64;
-  const void *f32_v2[2];  // second form: scalar / packed-add arithmetic
-  const void *f64_v2;
-  bool full_row;          // second form only: boxes without x halo covering whole rows
+  bool full_row;       // boxes without x halo covering whole rows
 };
 
-#define VARIANT(TY, RY, NBX, MINB) \
-  { TY, RY, NBX, (const void *)Star7Kernel<float, TY, RY, NBX, MINB>, \
-    (const void *)Star7Kernel<double, TY, RY, NBX, MINB>, \
-    {(const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 0, false>, \
-     (const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 1, false>}, \
-    (const void *)Star7KernelV2<double, TY, RY, NBX, MINB, 0, false>, false }
-#define VARIANT_FR(TY, RY, NBX, MINB) \
-  { TY, RY, NBX, nullptr, nullptr, \
-    {(const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 0, true>, \
-     (const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 1, true>}, \
-    (const void *)Star7KernelV2<double, TY, RY, NBX, MINB, 0, true>, true }
+#define VARIANT(TY, RY, NBX, MINB, FR) \
+  { TY, RY, NBX, \
+    {(const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 0, FR>, \
+     (const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 1, FR>}, \
+    (const void *)Star7KernelV2<double, TY, RY, NBX, MINB, 0, FR>, FR }
 
+// Tile shapes (chosen on the B200 by tools/tune_star7.py; shapes that were never selected have
+// been removed).  Index = option star7_variant.
 const VariantInfo kVariants[] = {
-    VARIANT(32, 4, 1, 2),  // 0: default
-    VARIANT(16, 2, 1, 3),  // 1
-    VARIANT(16, 2, 1, 4),  // 2
-    VARIANT(32, 4, 2, 1),  // 3
-    VARIANT(16, 2, 2, 1),  // 4
-    VARIANT(16, 4, 2, 2),  // 5
-    VARIANT(8, 2, 4, 1),   // 6
-    VARIANT(8, 1, 2, 2),   // 7
-    VARIANT(64, 8, 1, 1),  // 8
-    VARIANT(32, 2, 1, 1),  // 9
-    VARIANT(8, 2, 1, 4),   // 10
-    VARIANT(32, 8, 1, 2),  // 11
-    VARIANT_FR(8, 2, 4, 1),   // 12: full rows of 4 boxes (512 floats / 256 doubles)
-    VARIANT_FR(16, 4, 4, 1),  // 13
-    VARIANT_FR(16, 2, 2, 1),  // 14: full rows of 2 boxes
-    VARIANT_FR(8, 4, 8, 1),   // 15: full rows of 8 boxes (1024 floats)
-    VARIANT_FR(8, 2, 2, 2),   // 16
-    VARIANT_FR(16, 4, 2, 2),  // 17
-    VARIANT_FR(8, 1, 2, 1),   // 18
-    VARIANT_FR(8, 2, 1, 4),   // 19: one box
+    VARIANT(16, 2, 2, 1, false),  // 0: two haloed boxes x 16 rows: rows wider than 4 boxes, partial x domains
+    VARIANT(8, 2, 1, 4, false),   // 1: one haloed box x 8 rows: narrow partial domains
+    VARIANT(8, 2, 4, 1, true),    // 2: full rows of 4 boxes (512 floats / 256 doubles)
+    VARIANT(16, 2, 2, 1, true),   // 3: full rows of 2 boxes
+    VARIANT(8, 2, 1, 4, true),    // 4: full rows of one box
+    VARIANT(16, 4, 4, 1, true),   // 5: full rows of 4 boxes, 16-row tiles (tuning alternative)
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+constexpr int kVarHalo2 = 0, kVarHalo1 = 1, kVarFull4 = 2, kVarFull2 = 3, kVarFull1 = 4;
 
 template <typename T>
 size_t SmemBytes(const VariantInfo &v, int stages) {
@@ -594,38 +378,36 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   Star7Plan *p = new Star7Plan();
   p->is_double = dbl;
   const Options &o = rt->opt;
-  // Tile shape (measured on B200, tools/tune_star7.py, profiles/r1_tune_star7_512.csv):
-  // whenever a row fits 8 boxes the tile spans whole rows (no x halo, every plane of a
-  // tile one contiguous DRAM range) when a row fits 4 boxes: 8 rows x 4 boxes, 2 rows per thread, 6-deep ring,
-  // one CTA per SM reaches 5.8 TB/s at 512^3 fp32.  Wider rows use two haloed boxes x 16 rows.
+  // Tile shape (measured on B200, tools/tune_star7.py, profiles/r1_tune_star7_512.csv): whenever
+  // a row fits 4 boxes the tile spans whole rows (no x halo, every plane of a tile one contiguous
+  // DRAM range; 8 rows x 4 boxes, 2 rows per thread, 6-deep ring, one CTA per SM reaches 5.8 TB/s
+  // at 512^3 fp32).  Wider rows use two haloed boxes x 16 rows.
   int variant = o.star7_variant;
   const size_t row_bytes = (size_t)(dom.local_max[0] - dom.local_min[0]) * (dbl ? 8 : 4);
   const bool autov = variant < 0 || variant >= kNumVariants;
+  const int halo_variant = row_bytes >= 1024 ? kVarHalo2 : kVarHalo1;
   if (autov) {
     const int boxes = (int)((gin->ldim[0] * (size_t)(dbl ? 8 : 4) + 511) / 512);
     // (wider full-row tiles would need 4 rows per thread, which spills at 96 registers)
-    if (o.star7_impl == 0 || dom.local_min[0] != 0 || boxes > 4) variant = row_bytes >= 1024 ? 4 : 10;
-    else if (boxes <= 1) variant = 19;
-    else if (boxes == 2) variant = 14;
-    else variant = 12;
+    if (dom.local_min[0] != 0 || boxes > 4) variant = halo_variant;
+    else if (boxes <= 1) variant = kVarFull1;
+    else if (boxes == 2) variant = kVarFull2;
+    else variant = kVarFull4;
   }
   const int txb0 = dbl ? Geom<double>::TXB : Geom<float>::TXB;
   if (kVariants[variant].full_row) {
-    // needs the second form and a tile that spans the whole row
-    const bool fits = dom.local_min[0] == 0 && gin->ldim[0] <= kVariants[variant].nbx * txb0 &&
-                      o.star7_impl != 0;
+    // needs a tile that spans the whole row
+    const bool fits = dom.local_min[0] == 0 && gin->ldim[0] <= kVariants[variant].nbx * txb0;
     if (!fits) {
       if (!autov) { *why = "full-row tile shape does not span this grid's rows"; delete p; return nullptr; }
-      variant = row_bytes >= 1024 ? 4 : 10;
+      variant = halo_variant;
     }
   }
   const VariantInfo &v = kVariants[variant];
   p->variant = variant;
-  // star7_impl: 0 = first form, 1 = second form, 2 = second form with packed adds (fp32)
-  const int impl = o.star7_impl;
-  if (impl == 0) p->fn = dbl ? v.f64 : v.f32;
-  else p->fn = dbl ? v.f64_v2 : v.f32_v2[impl == 2 ? 1 : 0];
-  int stages = o.star7_stages > 0 ? std::min(o.star7_stages, kMaxStages) : (variant == 10 ? 5 : 6);
+  // star7_impl: 1 = scalar adds, 2 = packed adds (fp32 only; the default)
+  p->fn = dbl ? v.f64 : v.f32[o.star7_impl == 2 ? 1 : 0];
+  int stages = o.star7_stages > 0 ? std::min(o.star7_stages, kMaxStages) : (variant == kVarHalo1 ? 5 : 6);
   if (stages < 3) stages = 3;
   // deepest ring that fits the 227 KB of one SM
   while (stages > 3 && (dbl ? SmemBytes<double>(v, stages) : SmemBytes<float>(v, stages)) > 227 * 1024)
@@ -678,7 +460,6 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
     a->xbase = xbase;
     a->ntx = ntx; a->nty = nty; a->nzc = nzc; a->zc = zc; a->nitems = nitems;
     a->stages = stages;
-    a->l2_hint = o.star7_l2hint;
     a->st_hint = o.star7_sthint;
     using ET = typename std::remove_pointer<decltype(a->out)>::type;
     if (SlabPushTargets(rt, *gout, 0, (void **)&a->push_lo, (void **)&a->push_hi, sizeof(ET))) {
@@ -686,9 +467,11 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
       a->push_hi_z = gout->halo + gout->nz_loc - 1;
       p->pushes = true;
       // the halo stores are in the kernel, so its ordering with the neighbours can be too
-      if (o.star7_impl != 0 && rt->FillSlabSync(&a->sync)) {
+      if (rt->FillSlabSync(&a->sync)) {
         p->syncs = true;
-        SlabSyncSetBoundary(&a->sync, o.early_signal != 0, nzd, zc, nzc, ntx * nty, 1);
+        SlabSyncPlanEnds(&a->sync, o.early_signal != 0, nzd, &a->zc, &a->nzc, ntx * nty, 1, o.slab_zbl);
+        a->nitems = ntx * nty * a->nzc;
+        p->grid = std::min(a->nitems, slots);
       }
     }
   };

@@ -123,8 +123,8 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     for (int s = 0; s < NS; ++s) tma::mbar_init(&full[s], 1);
     tma::fence_barrier_init();
     tma::prefetch_tensormap(&tmap);
-    if (SLAB) SlabSyncWait(a.sync);  // before any halo plane is read or any peer halo written
   }
+  if (SLAB) SlabSyncWait(a.sync);  // before any halo plane is read or any peer halo written
 
   const int bx = warp % NBX;
   const int wy = warp / NBX;
@@ -240,21 +240,6 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const V o = v2::Vec7<FP>(a, c, wv, ev, sv, nv, bv, T1[r]); \
         if (st_ok[r]) StoreVec(reinterpret_cast<V *>(obase + (size_t)r * a.nx), o, a.st_hint != 0); \
       } \
-      if (SLAB) { \
-        /* the slab's first two / last two planes also go to the ring neighbours' halos: each \
-           thread forwards the vectors it has just stored (a rare path kept out of the row \
-           loop; a thread reading back its own stores needs no fence) */ \
-        const long long pushd = ((unsigned)(k - a.push_lo_z) < 2u) ? a.push_lo_delta \
-                              : ((unsigned)(k - a.push_hi_z) < 2u) ? a.push_hi_delta : 0ll; \
-        for (int e__ = pushd ? 1 : 0; e__ > 0; --e__) { \
-          _Pragma("unroll") for (int r = 0; r < RY; ++r) { \
-            if (st_ok[r]) { \
-              V *src__ = reinterpret_cast<V *>(obase + (size_t)r * a.nx); \
-              *reinterpret_cast<V *>(reinterpret_cast<char *>(src__) + pushd) = *src__; \
-            } \
-          } \
-        } \
-      } \
       obase += plane_elems; \
     } \
   } while (0)
@@ -317,21 +302,6 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const V bv = v2::Scale(c6, *reinterpret_cast<const V *>(bb + r * ROWB)); \
         const V o = v2::Sum7<FP>(q, wP, eP, pc, sv, nv, bv, T1[r]); \
         if (st_ok[r]) StoreVec(reinterpret_cast<V *>(obase + (size_t)r * a.nx), o, a.st_hint != 0); \
-      } \
-      if (SLAB) { \
-        /* the slab's first two / last two planes also go to the ring neighbours' halos: each \
-           thread forwards the vectors it has just stored (a rare path kept out of the row \
-           loop; a thread reading back its own stores needs no fence) */ \
-        const long long pushd = ((unsigned)(k - a.push_lo_z) < 2u) ? a.push_lo_delta \
-                              : ((unsigned)(k - a.push_hi_z) < 2u) ? a.push_hi_delta : 0ll; \
-        for (int e__ = pushd ? 1 : 0; e__ > 0; --e__) { \
-          _Pragma("unroll") for (int r = 0; r < RY; ++r) { \
-            if (st_ok[r]) { \
-              V *src__ = reinterpret_cast<V *>(obase + (size_t)r * a.nx); \
-              *reinterpret_cast<V *>(reinterpret_cast<char *>(src__) + pushd) = *src__; \
-            } \
-          } \
-        } \
       } \
       obase += plane_elems; \
     } \
@@ -434,7 +404,27 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         if (++k >= ze) break;
       }
     }
-    if (SLAB) SlabSyncItemDone(a.sync, item, PG::THREADS, threadIdx.x == 0);
+    if (SLAB) {
+      // The slab's first two / last two planes also go to the ring neighbours' halo planes: once
+      // the item is done, every thread forwards the vectors it stored itself for those planes
+      // (its own stores: no fence needed to read them back; they come from L2).  Kept out of the
+      // plane loop on purpose: any slab-specific code inside it made the compiler emit a larger
+      // and slower loop (+13 % per pass on ONE GPU with nothing to exchange).
+      for (int s = 0; s < 4; ++s) {
+        const int z = (s < 2 ? a.push_lo_z : a.push_hi_z) + (s & 1);
+        const long long delta = s < 2 ? a.push_lo_delta : a.push_hi_delta;
+        if (z < zb || z >= ze) continue;
+        const T *src = a.out + (ptrdiff_t)z * (ptrdiff_t)plane_elems + (ptrdiff_t)ybase * a.nx + x;
+#pragma unroll
+        for (int r = 0; r < RY; ++r) {
+          if (st_ok[r]) {
+            const V v = *reinterpret_cast<const V *>(src + (size_t)r * a.nx);
+            *reinterpret_cast<V *>(reinterpret_cast<char *>(const_cast<T *>(src + (size_t)r * a.nx)) + delta) = v;
+          }
+        }
+      }
+      SlabSyncItemDone(a.sync, item, PG::THREADS, threadIdx.x == 0);
+    }
   }
   if (SLAB) SlabSyncSignal(a.sync, PG::THREADS, threadIdx.x == 0);
 #undef SP_STEP
@@ -577,7 +567,9 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
     if (dbl) iso = (d0.scalars[i] == d0.scalars[0]);
     else iso = ((float)d0.scalars[i] == (float)d0.scalars[0]);
   }
-  const int ms = multi ? 1 : 0, fp = o.star7_impl == 2 ? 1 : 0;
+  // (debug_slab bit 2: the z-slab form of the kernel on one GPU, with nothing to exchange --
+  // a timing experiment that separates the form's code from the exchange itself)
+  const int ms = (multi || (o.debug_slab & 4)) ? 1 : 0, fp = o.star7_impl == 2 ? 1 : 0;
   if (iso) p->fn = dbl ? v.f64_iso[ms] : v.f32_iso[ms][fp];
   else p->fn = dbl ? v.f64[ms] : v.f32[ms][fp];
   p->iso = iso;
@@ -618,12 +610,15 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
     const int groups = slots / tiles;
     if (groups >= 2 && tiles * groups * 10 >= slots * 9) {
       const int b = o.star7_pair_zbl;
-      // a boundary CTA marches (b + 3) + (cs + 3) planes, an interior one cl + 3: make them equal
-      const int cs = (nz - 2 * b - (groups - 2) * (b + 3)) / groups;
+      // a boundary CTA marches (b + 3) + (cs + 3) planes and also pays for the peer stores and the
+      // system-scope fence before it signals (`bias` planes' worth), an interior one cl + 3: make
+      // them equal
+      const int bias = std::max(0, o.star7_pair_zbias);
+      const int cs = (nz - 2 * b - (groups - 2) * (b + 3 + bias)) / groups;
       if (cs >= 4) {
         zbl = b;
         nlong = groups - 2;
-        clong = cs + b + 3;
+        clong = cs + b + 3 + bias;
         cshort = CeilDiv(nz - 2 * b - nlong * clong, 2);
         nzc = groups + 2;
         nitems = tiles * nzc;
@@ -663,6 +658,9 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
         a->sync.nb_lo = a->sync.nb_hi = 0;
       }
       a->zbl = zbl; a->nlong = nlong; a->clong = clong; a->cshort = cshort;
+      // timing experiments only (results are wrong): what the exchange costs the kernel
+      if (o.debug_slab & 1) { a->push_lo_z = a->push_hi_z = -(1 << 30); a->push_lo_delta = a->push_hi_delta = 0; }
+      if (o.debug_slab & 2) { a->sync.flags = nullptr; a->sync.done = nullptr; a->sync.boundary_items = 0; }
       if (multi) {
         const Grid *go = gout[dir];
         const MemberLayout &ml = go->members[0];

@@ -75,6 +75,11 @@ struct SlabSync {
   // 0: publish when the whole sweep is done.
   int boundary_items;
   int nb_lo, nb_hi;
+  // single sweeps: when > 0 the slab's first and last `zbl` planes are chunks of their own
+  // (chunk sequence 0 and 1), followed by the interior in chunks of the kernel's zc planes: the
+  // boundary work is over -- halo planes delivered, fences paid, number published -- a fraction
+  // of a sweep after the launch, and the interior chunks carry none of it
+  int zbl;
 };
 
 // Host side: which chunks are boundary chunks.  `reach` = planes a sweep reads beyond / delivers
@@ -83,6 +88,7 @@ struct SlabSync {
 inline void SlabSyncSetBoundary(SlabSync *s, bool early, int nz, int zc, int nzc, int tiles, int reach) {
   s->boundary_items = 0;
   s->nb_lo = s->nb_hi = 0;
+  s->zbl = 0;
   if (!early || !s->done) return;
   const int last = nz - (nzc - 1) * zc;
   int lo = (reach + zc - 1) / zc;                       // chunks covering the first `reach` planes
@@ -96,12 +102,49 @@ inline void SlabSyncSetBoundary(SlabSync *s, bool early, int nz, int zc, int nzc
   s->boundary_items = (lo + hi) * tiles;
 }
 
+// Single sweeps on a z-slab: short boundary chunks first.  Rewrites the chunking (*zc, *nzc) of
+// a domain of `nz` planes when the slab is thick enough; falls back to SlabSyncSetBoundary.
+inline void SlabSyncPlanEnds(SlabSync *s, bool early, int nz, int *zc, int *nzc, int tiles, int reach,
+                             int zbl) {
+  if (early && s->done && zbl >= reach && nz >= 2 * zbl + 8) {
+    const int interior = nz - 2 * zbl;
+    const int nint = (interior + *zc - 1) / *zc;
+    *zc = (interior + nint - 1) / nint;
+    *nzc = 2 + nint;
+    s->boundary_items = 2 * tiles;
+    s->nb_lo = s->nb_hi = 0;
+    s->zbl = zbl;
+    return;
+  }
+  SlabSyncSetBoundary(s, early, nz, *zc, *nzc, tiles, reach);
+}
+
+// planes [*zb, *ze) of the work item with chunk sequence number `seq` (single-sweep kernels)
+__device__ __forceinline__ void SlabChunkRange(const SlabSync &s, int seq, int nzc, int zc, int dz0, int dz1,
+                                               int *zb, int *ze);
+
 // z chunk a work item with chunk sequence number `seq` processes: the nb_lo lowest chunks, the
 // nb_hi highest, then the interior ones in order
 __host__ __device__ __forceinline__ int SlabChunkOrder(const SlabSync &s, int seq, int nzc) {
   const int nb = s.nb_lo + s.nb_hi;
   if (nb == 0) return seq;
   return seq < s.nb_lo ? seq : (seq < nb ? nzc - nb + seq : seq - s.nb_hi);
+}
+
+__device__ __forceinline__ void SlabChunkRange(const SlabSync &s, int seq, int nzc, int zc, int dz0, int dz1,
+                                               int *zb, int *ze) {
+  if (s.zbl > 0) {
+    if (seq < 2) {
+      *zb = seq == 0 ? dz0 : dz1 - s.zbl;
+      *ze = *zb + s.zbl;
+    } else {
+      *zb = dz0 + s.zbl + (seq - 2) * zc;
+      *ze = min(*zb + zc, dz1 - s.zbl);
+    }
+  } else {
+    *zb = dz0 + SlabChunkOrder(s, seq, nzc) * zc;
+    *ze = min(*zb + zc, dz1);
+  }
 }
 
 __device__ __forceinline__ uint32_t LdAcquireSys(const uint32_t *p) {
@@ -122,9 +165,8 @@ __device__ __forceinline__ unsigned long long GlobalTimerNs() {
 // Spins until both flag words have reached `epoch`.  A lost signal becomes an error the host
 // reports (which neighbour, which sweep, what was seen), not a hang and not a dead context:
 // the bound is wall time (option sync_timeout_s), so profiler serialisation or ranks
-// time-slicing one GPU do not trip it.  Out of line: the spin loop must not take part in the
-// sweeps' register allocation.
-static __device__ __noinline__ void SlabWaitFlags(const uint32_t *flags, uint32_t epoch,
+// time-slicing one GPU do not trip it.
+static __device__ __forceinline__ void SlabWaitFlags(const uint32_t *flags, uint32_t epoch,
                                                   unsigned long long timeout_ns, uint32_t *err) {
   for (int i = 0; i < 2; ++i) {
     uint32_t spins = 0;
@@ -151,11 +193,17 @@ static __device__ __noinline__ void SlabWaitFlags(const uint32_t *flags, uint32_
   }
 }
 
-// Called by thread 0 of every CTA before the CTA's first __syncthreads().  Only CTAs that
-// will process a boundary item need the neighbours: an interior item reads and writes nothing but
-// this rank's own interior planes, which stream order already protects.  Items are visited in
-// increasing order and the boundary items come first, so a CTA whose first item is interior never
-// meets one.
+// Called by EVERY thread of a CTA before it touches a halo plane, and executed by every thread:
+// each thread polls the two flag words itself (a warp's loads of one address are one request, so
+// a CTA polls with one request per warp).  Deliberately not "thread 0 waits, the rest wait at the
+// barrier": a spin loop under any thread-dependent condition in front of the sweep loop made the
+// compiler treat the loop as possibly diverged -- it cloned a step and wrapped the shuffles in
+// convergence barriers (4272 SASS instructions against 2648), and the z-slab form of the fused
+// pass ran 13 % slower than the single-GPU form on ONE GPU with nothing to exchange.  Only CTAs
+// that will process a boundary item need the neighbours: an interior item reads and writes
+// nothing but this rank's own interior planes, which stream order already protects.  Items are
+// visited in increasing order and the boundary items come first, so a CTA whose first item is
+// interior never meets one.
 __device__ __forceinline__ void SlabSyncWait(const SlabSync &s) {
   if (!s.flags) return;
   if (s.boundary_items > 0 && (int)blockIdx.x >= s.boundary_items) return;
@@ -163,10 +211,12 @@ __device__ __forceinline__ void SlabSyncWait(const SlabSync &s) {
     const unsigned long long t0 = GlobalTimerNs();
     SlabWaitFlags(s.flags, s.wait_epoch, s.timeout_ns, s.err);
     const unsigned long long dt = GlobalTimerNs() - t0;
-    atomicAdd(s.prof + 0, dt);
-    atomicMax(s.prof + 1, dt);
-    atomicAdd(s.prof + 2, 1ull);
-    if (blockIdx.x == 0) atomicAdd(s.prof + 3, 1ull);
+    if (threadIdx.x == 0) {
+      atomicAdd(s.prof + 0, dt);
+      atomicMax(s.prof + 1, dt);
+      atomicAdd(s.prof + 2, 1ull);
+      if (blockIdx.x == 0) atomicAdd(s.prof + 3, 1ull);
+    }
     return;
   }
   SlabWaitFlags(s.flags, s.wait_epoch, s.timeout_ns, s.err);
@@ -176,9 +226,14 @@ __device__ __forceinline__ void SlabSyncWait(const SlabSync &s) {
 // of the boundary items to finish publishes the sweep's number to both neighbours.
 __device__ __forceinline__ void SlabSyncItemDone(const SlabSync &s, int item, int nthreads, bool leader) {
   if (!s.done || item >= s.boundary_items) return;
-  __threadfence_system();  // this thread's stores (incl. peer stores) are visible system-wide
+  // every consumer's stores (incl. the peer stores) precede the barrier; the leader's
+  // system-scope fence after it then orders all of them before the counter and the flags
+  // (fence cumulativity -- the pattern of a grid-wide barrier: bar.sync, one thread fences and
+  // signals).  One fence per CTA instead of one per thread: a fence waits for the acknowledgement
+  // of the thread's outstanding NVLink stores.
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
   if (leader) {
+    __threadfence_system();
     const unsigned prev = atomicAdd(s.done, 1u);
     if (prev == (unsigned)s.boundary_items - 1u) {
       *s.done = 0;           // next launch starts from zero (stream order)
@@ -194,9 +249,9 @@ __device__ __forceinline__ void SlabSyncItemDone(const SlabSync &s, int item, in
 // items the number has already been published by SlabSyncItemDone.)
 __device__ __forceinline__ void SlabSyncSignal(const SlabSync &s, int nthreads, bool leader) {
   if (!s.done || s.boundary_items > 0) return;
-  __threadfence_system();  // this thread's stores (incl. peer stores) are visible system-wide
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
   if (leader) {
+    __threadfence_system();  // all consumers' stores (incl. peer stores), ordered by the barrier
     const unsigned prev = atomicAdd(s.done, 1u);
     if (prev == gridDim.x - 1) {
       *s.done = 0;           // next launch starts from zero (stream order)

@@ -28,7 +28,7 @@ co = [0.1] * 6 + [0.4]
 r = api.rt()
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 rows = []
-variants = [int(v) for v in os.environ.get('TUNE_VARIANTS', ','.join(str(i) for i in range(20))).split(',')]
+variants = [int(v) for v in os.environ.get('TUNE_VARIANTS', ','.join(str(i) for i in range(6))).split(',')]
 stages = [4, 5, 6, 8]
 zcs = [16, 32, 64, 128]
 hints = [(0, 0), (1, 0), (0, 1), (1, 1)]
@@ -39,7 +39,6 @@ def measure(v, s, zc, l2, st, occ=0):
     api.set_option(f"star7_variant={v}")
     api.set_option(f"star7_stages={s}")
     api.set_option(f"star7_zc={zc}")
-    api.set_option(f"star7_l2hint={l2}")
     api.set_option(f"star7_sthint={st}")
     api.set_option(f"star7_occ={occ}")
     lib.run_sweeps_only_physis(4, n, n, n, *co)
