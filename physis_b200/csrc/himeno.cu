@@ -328,18 +328,15 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
   // groups of four, so 7+1 (two CTAs per SM) and 15+1 fill the register file where
   // 8+1 strands three warps' worth.
   int TY = rt->opt.himeno_by;
-  if (TY != 7 && TY != 8 && TY != 11 && TY != 15) TY = 15;  // measured best (profiles/r1_tune_himeno_XL.csv)
+  if (TY != 7 && TY != 15) TY = 15;  // measured best (profiles/r1_tune_himeno_XL.csv); 7: two CTAs per SM
   int stages = rt->opt.himeno_stages > 0 ? std::min(rt->opt.himeno_stages, kMaxStages) : 6;
   if (stages < 4) stages = 4;
-  switch (TY) {
-    case 7: p->fn = gosa ? (const void *)HimenoKernel<7, true> : (const void *)HimenoKernel<7, false>;
-      p->smem = SmemBytes<7>(stages); break;
-    case 8: p->fn = gosa ? (const void *)HimenoKernel<8, true> : (const void *)HimenoKernel<8, false>;
-      p->smem = SmemBytes<8>(stages); break;
-    case 11: p->fn = gosa ? (const void *)HimenoKernel<11, true> : (const void *)HimenoKernel<11, false>;
-      p->smem = SmemBytes<11>(stages); break;
-    default: p->fn = gosa ? (const void *)HimenoKernel<15, true> : (const void *)HimenoKernel<15, false>;
-      p->smem = SmemBytes<15>(stages); break;
+  if (TY == 7) {
+    p->fn = gosa ? (const void *)HimenoKernel<7, true> : (const void *)HimenoKernel<7, false>;
+    p->smem = SmemBytes<7>(stages);
+  } else {
+    p->fn = gosa ? (const void *)HimenoKernel<15, true> : (const void *)HimenoKernel<15, false>;
+    p->smem = SmemBytes<15>(stages);
   }
   p->block = (TY + 1) * 32;
   PSB_CUDA(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));

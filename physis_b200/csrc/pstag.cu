@@ -209,28 +209,20 @@ PstagKernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant_
   // this thread's 3 x (RY+1) vertices of kap plane KZ, which arrived in ring slot SLOT: patch
   // row q has flat row number R = KZ*ky + ytile + q; the rows with even R are in the first
   // box, those with odd R in the second (whose first wanted column is `kodd` elements in),
-  // and in either box row q is row q/2.  A thread wants the three vertices x, x+1, x+2 of a row,
-  // its lane neighbour x+2, x+3, x+4: one conflict-free 16-byte load per thread fetches a
-  // pair, the rest comes from the next lane by shuffle (8-byte loads at this 16-byte lane
-  // stride are two-way bank conflicts: ncu counted 20 M of them per sweep); lane 31 loads the
-  // pair after its own instead.  Which pair a thread loads depends on the row's parity
-  // (warp-uniform): the wanted vertices start at the pair's first or second element.
+  // and in either box row q is row q/2.  (8-byte loads at a 16-byte lane stride are two-way bank
+  // conflicts, 20 M per sweep in ncu; fetching pairs with one 16-byte load and taking the third
+  // vertex from the next lane by shuffle removed them but added 50 M instructions and 23
+  // registers, and the sweep was no faster -- it is bound by fp64 dependency latency at two
+  // consumer warps per scheduler, not by shared-memory bandwidth -- so the simple form stays.)
 #define PS_LOAD_KAP(K, SLOT, KZ) do { \
     const unsigned char *kp__ = my_kap + (SLOT) * STAGE_BYTES; \
     const int p0__ = ((KZ) * a.ky + ytile) & 1; \
     _Pragma("unroll") for (int r = 0; r <= RY; ++r) { \
       const int q__ = row0 + r; \
       const int odd__ = (p0__ + q__) & 1; \
-      const unsigned char *row__ = kp__ + odd__ * (L::KAP_ODD - L::KAP) + (q__ >> 1) * KROW; \
-      const double2 v__ = *reinterpret_cast<const double2 *>(row__); \
-      double nx__ = __shfl_down_sync(0xffffffffu, v__.x, 1); \
-      double ny__ = __shfl_down_sync(0xffffffffu, v__.y, 1); \
-      if (lane_last) { \
-        const double2 w__ = *reinterpret_cast<const double2 *>(row__ + 16); \
-        nx__ = w__.x; ny__ = w__.y; \
-      } \
-      if (odd__ * kodd) { K[r][0] = v__.y; K[r][1] = nx__; K[r][2] = ny__; } \
-      else { K[r][0] = v__.x; K[r][1] = v__.y; K[r][2] = nx__; } \
+      const double *src__ = reinterpret_cast<const double *>( \
+          kp__ + odd__ * (L::KAP_ODD - L::KAP) + (q__ >> 1) * KROW) + odd__ * kodd; \
+      K[r][0] = src__[0]; K[r][1] = src__[1]; K[r][2] = src__[2]; \
     } \
   } while (0)
   // One plane z: the centre plane is in registers (CEN) and in slot CS, the top plane arrives
@@ -381,20 +373,8 @@ struct PstagVariant {
   { TY, RY, NBX, MINB, (const void *)PstagKernel<TY, RY, NBX, MINB, 6>, \
     (const void *)PstagKernel<TY, RY, NBX, MINB, 3>, (size_t)PstagBoxStride<TY>() }
 const PstagVariant kPstagVariants[] = {
-    PSTAG_VARIANT(16, 2, 2, 1),  // 0: 16 consumer warps (register-capped at 96: spills)
-    PSTAG_VARIANT(8, 2, 2, 1),   // 1: 8 consumer warps
-    PSTAG_VARIANT(16, 2, 1, 1),  // 2
-    PSTAG_VARIANT(8, 1, 2, 1),   // 3
-    PSTAG_VARIANT(8, 2, 1, 2),   // 4: 4 consumer warps, 128 registers, two CTAs per SM
-    PSTAG_VARIANT(16, 4, 2, 1),  // 5
-    PSTAG_VARIANT(8, 2, 1, 3),   // 6: same shape squeezed to three CTAs per SM
-    PSTAG_VARIANT(8, 2, 1, 4),   // 7: ... four
-    PSTAG_VARIANT(8, 1, 1, 2),   // 8: 8 consumer warps of one row each
-    PSTAG_VARIANT(4, 1, 1, 4),   // 9
-    PSTAG_VARIANT(16, 4, 1, 3),  // 10: 4 consumer warps, 4 rows per thread
-    PSTAG_VARIANT(16, 2, 1, 2),  // 11: 8 consumer warps, two CTAs per SM
-    PSTAG_VARIANT(8, 2, 2, 2),   // 12: 8 consumer warps over two boxes, two CTAs per SM
-    PSTAG_VARIANT(4, 2, 1, 4),   // 13: 2 consumer warps, four CTAs per SM
+    PSTAG_VARIANT(4, 2, 1, 4),  // 0: 2 consumer warps, four CTAs per SM (measured best, profiles/r1_tune_pstag_512.csv)
+    PSTAG_VARIANT(8, 2, 1, 2),  // 1: 4 consumer warps, two CTAs per SM (within 1-3 % of it)
 };
 constexpr int kNumPstagVariants = sizeof(kPstagVariants) / sizeof(kPstagVariants[0]);
 
@@ -447,9 +427,9 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
     *why = "x extent and domain x-range must be even"; return nullptr;
   }
   int vi = rt->opt.pstag_variant;
-  if (vi < 0 || vi >= kNumPstagVariants) vi = 13;
+  if (vi < 0 || vi >= kNumPstagVariants) vi = 0;
   // grids whose y extent is not a multiple of the chosen tile height try 4 rows
-  if (ny % kPstagVariants[vi].ty != 0 && ny % 4 == 0) vi = 13;
+  if (ny % kPstagVariants[vi].ty != 0 && ny % 4 == 0) vi = 0;
   const PstagVariant &V = kPstagVariants[vi];
   const int kTY = V.ty, kRY = V.ry, kNBX = V.nbx;
   if (ny % kTY != 0 || (dom.local_min[1] % kTY) != 0) { *why = "y extent must be a multiple of the tile height"; return nullptr; }

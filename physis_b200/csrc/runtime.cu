@@ -453,7 +453,6 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "star7_zc") o->star7_zc = (int)val;
   else if (k == "star7_occ") o->star7_occ = (int)val;
   else if (k == "star7_variant") o->star7_variant = (int)val;
-  else if (k == "star7_impl") o->star7_impl = (int)val;
   else if (k == "star7_sthint") o->star7_sthint = (int)val;
   else if (k == "star7_fuse") o->star7_fuse = (int)val;
   else if (k == "star7_pair_zc") o->star7_pair_zc = (int)val;

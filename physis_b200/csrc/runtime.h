@@ -164,9 +164,9 @@ class GridSpace {
 
 struct Options {
   // star-7 sweep: tile shape (index into star7.cu's table, -1 = automatic), ring depth, z chunk,
-  // resident CTAs (0 = automatic), streaming stores, arithmetic form (1 scalar / 2 packed adds)
+  // resident CTAs (0 = automatic), streaming stores
   int star7_stages = 0, star7_zc = 0, star7_occ = 0;
-  int star7_variant = -1, star7_sthint = 0, star7_impl = 2;
+  int star7_variant = -1, star7_sthint = 0;
   int star7_fuse = 1;     // 1: a ping-pong pair of whole-grid 7-pt sweeps runs as one fused two-sweep pass
   int star7_pair_zc = 0;  // z chunk of the fused kernel; 0 = automatic
   int star7_pair_zbl = 8;       // multi-GPU: planes of the boundary chunks that run first (0: equal chunks)
@@ -180,7 +180,7 @@ struct Options {
   int himeno_pair_zc = 0;   // z chunk of the fused Himeno kernel; 0 = automatic
   int himeno_pair_pf = 1;   // planes ahead the coefficient rows are prefetched into L2
   int pstag_push = 0;     // 1: the config-5 sweep stores its halo planes and orders itself in the kernel
-  int pstag_variant = 13 /* measured best, profiles/r1_tune_pstag_512.csv */, pstag_stages = 0, pstag_occ = 0;
+  int pstag_variant = 0 /* index into pstag.cu's tile shapes */, pstag_stages = 0, pstag_occ = 0;
   int time_kernels = 0;        // per-family CUDA-event timing (for bench roofline)
   size_t stage_chunk = 64u << 20;  // pinned staging chunk for pageable copies
   int copy_threads = 0;            // host threads that fill / drain a staging chunk (0 = automatic:

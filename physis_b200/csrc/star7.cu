@@ -284,15 +284,14 @@ Star7KernelV2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
 
 struct VariantInfo {
   int ty, ry, nbx;
-  const void *f32[2];  // scalar / packed-add arithmetic
+  const void *f32;     // packed adds
   const void *f64;
   bool full_row;       // boxes without x halo covering whole rows
 };
 
 #define VARIANT(TY, RY, NBX, MINB, FR) \
   { TY, RY, NBX, \
-    {(const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 0, FR>, \
-     (const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 1, FR>}, \
+    (const void *)Star7KernelV2<float, TY, RY, NBX, MINB, 1, FR>, \
     (const void *)Star7KernelV2<double, TY, RY, NBX, MINB, 0, FR>, FR }
 
 // Tile shapes (chosen on the B200 by tools/tune_star7.py; shapes that were never selected have
@@ -405,8 +404,7 @@ Star7Plan *PrepareStar7(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   }
   const VariantInfo &v = kVariants[variant];
   p->variant = variant;
-  // star7_impl: 1 = scalar adds, 2 = packed adds (fp32 only; the default)
-  p->fn = dbl ? v.f64 : v.f32[o.star7_impl == 2 ? 1 : 0];
+  p->fn = dbl ? v.f64 : v.f32;
   int stages = o.star7_stages > 0 ? std::min(o.star7_stages, kMaxStages) : (variant == kVarHalo1 ? 5 : 6);
   if (stages < 3) stages = 3;
   // deepest ring that fits the 227 KB of one SM

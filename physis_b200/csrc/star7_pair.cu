@@ -441,27 +441,21 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 
 struct PairVariant {
   int nbx, nwy, ry, minb;
-  const void *f32[2][2];  // [one GPU / z-slab][scalar / packed-add arithmetic]
-  const void *f64[2];
-  const void *f32_iso[2][2];  // equal neighbour coefficients
-  const void *f64_iso[2];
+  const void *f32[2][2];  // [one GPU / z-slab][general / equal neighbour coefficients], packed adds
+  const void *f64[2][2];
   int smem_f32, smem_f64, threads;
 };
 
 #define PAIR_VARIANT(NBX, NWY, RY, MINB) \
   { NBX, NWY, RY, MINB, \
-    {{(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0, false, false>, \
-      (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, false, false>}, \
-     {(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0, true, false>, \
-      (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, true, false>}}, \
-    {(const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, false, false>, \
-     (const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, true, false>}, \
-    {{(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0, false, true>, \
+    {{(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, false, false>, \
       (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, false, true>}, \
-     {(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 0, true, true>, \
+     {(const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, true, false>, \
       (const void *)Star7PairKernel<float, NBX, NWY, RY, MINB, 1, true, true>}}, \
-    {(const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, false, true>, \
-     (const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, true, true>}, \
+    {{(const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, false, false>, \
+      (const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, false, true>}, \
+     {(const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, true, false>, \
+      (const void *)Star7PairKernel<double, NBX, NWY, RY, MINB, 0, true, true>}}, \
     PairGeom<float, NBX, NWY, RY>::SMEM, PairGeom<double, NBX, NWY, RY>::SMEM, NBX * NWY * 32 }
 
 const PairVariant kPairVariants[] = {
@@ -569,9 +563,8 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
   }
   // (debug_slab bit 2: the z-slab form of the kernel on one GPU, with nothing to exchange --
   // a timing experiment that separates the form's code from the exchange itself)
-  const int ms = (multi || (o.debug_slab & 4)) ? 1 : 0, fp = o.star7_impl == 2 ? 1 : 0;
-  if (iso) p->fn = dbl ? v.f64_iso[ms] : v.f32_iso[ms][fp];
-  else p->fn = dbl ? v.f64[ms] : v.f32[ms][fp];
+  const int ms = (multi || (o.debug_slab & 4)) ? 1 : 0;
+  p->fn = dbl ? v.f64[ms][iso ? 1 : 0] : v.f32[ms][iso ? 1 : 0];
   p->iso = iso;
   p->smem = dbl ? v.smem_f64 : v.smem_f32;
   p->block = v.threads;

@@ -45,7 +45,7 @@ def case_pair():
     iso64 = np.array([0.1234567] * 6 + [0.2592598])   # equal neighbour coefficients: shared-product form
     cases = [((128, 32, 16), 3, np.float32, (), co64), ((256, 20, 33), 5, np.float32, ("star7_pair_zc=3",), co64),
              ((512, 17, 24), 4, np.float32, (), iso64), ((64, 30, 19), 6, np.float64, ("star7_pair_zc=2",), co64),
-             ((384, 9, 41), 3, np.float32, ("star7_impl=1",), co64), ((128, 21, 26), 5, np.float64, (), iso64),
+             ((384, 9, 41), 3, np.float32, (), co64), ((128, 21, 26), 5, np.float64, (), iso64),
              ((256, 12, 35), 4, np.float32, ("star7_pair_zc=6",), iso64),
              # rows wider than one fused tile: x tiles
              ((1024, 14, 32), 3, np.float32, (), iso64), ((768, 11, 40), 4, np.float32, ("star7_pair_zc=3",), co64),

@@ -55,8 +55,8 @@ def _run_pair(shape, iters, dtype, options=(), coeffs=None):
     ((200, 29, 9), 3, ("star7_pair_zc=1",)),
     ((64, 5, 6), 4, ()),
     ((4, 2, 2), 3, ()),
-    ((512, 128, 64), 3, ("star7_impl=1",)),
-    ((256, 15, 33), 7, ("star7_impl=1", "star7_pair_zc=8")),
+    ((512, 128, 64), 3, ()),
+    ((256, 15, 33), 7, ("star7_pair_zc=8",)),
     # rows wider than one tile: x tiles with one-vector seams (BASELINE config 4's 1024 floats)
     ((1024, 40, 24), 3, ()),
     ((1024, 64, 64), 5, ()),
@@ -126,7 +126,7 @@ def test_unfused_schedule_unchanged():
     ((128, 30, 17), 5, ("star7_pair_zc=4",)),
     ((200, 29, 9), 3, ("star7_pair_zc=1",)),
     ((64, 5, 6), 4, ()),
-    ((256, 15, 33), 7, ("star7_impl=1", "star7_pair_zc=8")),
+    ((256, 15, 33), 7, ("star7_pair_zc=8",)),
     ((256, 47, 20), 3, ("star7_iso=0",)),
     ((1024, 31, 20), 3, ()),
     ((1536, 18, 7), 4, ("star7_pair_zc=2",)),

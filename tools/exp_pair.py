@@ -22,11 +22,10 @@ if len(sys.argv) > 1:
 count = int(os.environ.get("EXP_COUNT", "200"))
 configs = [("star7_fuse=0",)]
 if os.environ.get("EXP_CONFIGS") == "short":
-    configs += [("star7_fuse=1",), ("star7_fuse=1", "star7_impl=1"), ("star7_fuse=1", "star7_pair_zc=64")]
+    configs += [("star7_fuse=1",), ("star7_fuse=1", "star7_pair_zc=64")]
 else:
-    for impl in (2, 1):
-        for zc in (0, 32, 64, 128, 256):
-            configs.append(("star7_fuse=1", f"star7_impl={impl}", f"star7_pair_zc={zc}"))
+    for zc in (0, 32, 64, 128, 256):
+        configs.append(("star7_fuse=1", f"star7_pair_zc={zc}"))
 for (nx, ny, nz) in shapes:
     f0 = np.random.default_rng(0).random(nx * ny * nz, dtype=np.float32)
     for cfg in configs:

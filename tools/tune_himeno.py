@@ -21,7 +21,7 @@ lib.himeno_sweeps_only.argtypes = [C.c_int, C.c_int]
 r = api.rt()
 pts = (mi - 2) * (mj - 2) * (mk - 2)
 rows = []
-for by, st, zc, occ, gosa in itertools.product([7, 8, 11, 15], [4, 6, 8], [0, 32, 64], [0, 1], [0]):
+for by, st, zc, occ, gosa in itertools.product([7, 15], [4, 6, 8], [0, 32, 64], [0, 1], [0]):
     api.set_option(f"himeno_by={by}")
     api.set_option(f"himeno_stages={st}")
     api.set_option(f"himeno_zc={zc}")

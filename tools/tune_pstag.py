@@ -24,7 +24,7 @@ lib.pstag_copyin_local(u.ctypes.data, kap.ctypes.data)
 lib.pstag_sweeps_only.argtypes = [C.c_int] * 4
 r = api.rt()
 rows = []
-VARIANTS = [int(x) for x in os.environ.get("PSTAG_VARIANTS", "4,13,8,1,6,11").split(",")]
+VARIANTS = [int(x) for x in os.environ.get("PSTAG_VARIANTS", "0,1").split(",")]
 STAGES = [int(x) for x in os.environ.get("PSTAG_STAGES", "3,6").split(",")]
 OCCS = [int(x) for x in os.environ.get("PSTAG_OCCS", "0,1,2,3,4").split(",")]
 for v, st, occ in itertools.product(VARIANTS, STAGES, OCCS):

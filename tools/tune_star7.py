@@ -35,7 +35,6 @@ hints = [(0, 0), (1, 0), (0, 1), (1, 1)]
 
 
 def measure(v, s, zc, l2, st, occ=0):
-    api.set_option(f"star7_impl={os.environ.get('TUNE_IMPL', '2')}")
     api.set_option(f"star7_variant={v}")
     api.set_option(f"star7_stages={s}")
     api.set_option(f"star7_zc={zc}")
