@@ -47,6 +47,7 @@
 
 #include <algorithm>
 #include <string>
+#include <vector>
 
 namespace physis_b200 {
 
@@ -65,8 +66,16 @@ struct HimenoPairArgs {
   int nx, ny, nz;
   int nty, ntx, nzc, zc, nitems;
   int tx0[kHpMaxXTiles], txs[kHpMaxXTiles], txe[kHpMaxXTiles];
-  int dz0, dz1;  // planes written: [1, nz-1)
+  int dz0, dz1;  // planes written (local indices): the global interior [1, n-1) cut to this rank's slab
   int pf;        // coefficient prefetch distance in planes
+  // z-slab view (multi-GPU; on one GPU the faces are planes 0 and nz-1 and nothing is pushed): local
+  // planes holding the global z faces (-1 when they are elsewhere), whose cells no sweep updates;
+  // the slab's first two / last two planes are also stored into the ring neighbours' halo planes
+  // (byte distances from the plane's own address in `out`)
+  int zface_lo, zface_hi;
+  int push_lo_z, push_hi_z;
+  long long push_lo_delta, push_hi_delta;
+  SlabSync sync;
 };
 
 __device__ __forceinline__ void PrefetchL2(const void *p, uint32_t bytes) {
@@ -139,7 +148,8 @@ struct HpGeom {
 };
 
 // H rows per tile = consumer warps; no producer warp (thread 0 issues the TMA loads).
-template <int H>
+// SLAB: the z-slab form (halo planes forwarded to the ring neighbours, ordering with them).
+template <int H, bool SLAB>
 __global__ void __launch_bounds__(H * 32, 1)
 HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ HimenoPairArgs a) {
   using G = Geom<float>;
@@ -162,6 +172,7 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     tma::fence_barrier_init();
     tma::prefetch_tensormap(&tmap);
   }
+  if (SLAB) SlabSyncWait(a.sync);  // before any halo plane is read or any peer halo written
 
   // this thread's vector inside a stage: row warp+1 (row 0 is the halo row above the tile),
   // column 16 bytes of x halo + lane * 16
@@ -175,8 +186,9 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   };
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-    const int zci = item / tiles_xy;
-    const int txy = item - zci * tiles_xy;
+    const int zseq = item / tiles_xy;
+    const int zci = SLAB ? SlabChunkOrder(a.sync, zseq, a.nzc) : zseq;
+    const int txy = item - zseq * tiles_xy;
     const int ty = txy / a.ntx;
     const int tx = txy - ty * a.ntx;
     const int xt0 = a.tx0[tx];
@@ -219,7 +231,7 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     // pull the coefficient rows of the first planes towards L2 (one array per lane)
     if (lane < 12 && ld_row) {
       const uint32_t bytes = (uint32_t)min(G::TXB, a.nx - xt0) * 4u;
-      for (int m = max(zb - 1, 1); m < min(zb - 1 + a.pf, a.nz - 1); ++m)
+      for (int m = max(zb - 1, 0); m < min(zb - 1 + a.pf, a.nz); ++m)
         PrefetchL2(a.coef[lane] + (size_t)m * plane_elems + (size_t)y * a.nx + xt0, bytes);
     }
 
@@ -237,7 +249,7 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       const int m = k + 1;  // plane whose first-sweep values this step computes
       const int slot_c = (slot_b + 1 == kHpInSlots) ? 0 : slot_b + 1;
       const int slot_t = (slot_c + 1 == kHpInSlots) ? 0 : slot_c + 1;
-      const bool plane_upd = (m >= 1) && (m < a.nz - 1);
+      const bool plane_upd = (m != a.zface_lo) && (m != a.zface_hi) && (m >= 0) && (m < a.nz);
       const size_t gm = (size_t)m * plane_elems + gp;
       // ---- first sweep: s1(m) from p(m-1), p(m), p(m+1) ---------------------------------
       float4 q[12];
@@ -250,7 +262,7 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
           if (ld_ok) q[c] = __ldg(reinterpret_cast<const float4 *>(a.coef[c] + gm));
         // and the row of plane m + pf towards L2
         const int mp = m + a.pf;
-        if (a.pf > 0 && lane < 12 && mp < a.nz - 1 && mp <= ze)
+        if (a.pf > 0 && lane < 12 && mp < a.nz && mp <= ze)
           PrefetchL2(a.coef[lane] + (size_t)mp * plane_elems + (size_t)y * a.nx + xt0,
                      (uint32_t)min(G::TXB, a.nx - xt0) * 4u);
       }
@@ -297,34 +309,58 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       for (int c = 0; c < 12; ++c) hold[c] = q[c];
       slot_b = slot_c;
     }
+    if (SLAB) {
+      // the slab's first two / last two planes also go to the ring neighbours' halo planes: once
+      // the item is done every thread forwards the cells it stored itself (outside the plane loop,
+      // as in star7_pair.cu)
+      for (int s = 0; s < 4; ++s) {
+        const int z = (s < 2 ? a.push_lo_z : a.push_hi_z) + (s & 1);
+        const long long delta = s < 2 ? a.push_lo_delta : a.push_hi_delta;
+        if (z < zb || z >= ze || !st_any) continue;
+        float *src = a.out + (size_t)z * plane_elems + gp;
+        if (st_all) {
+          *reinterpret_cast<float4 *>(reinterpret_cast<char *>(src) + delta) = *reinterpret_cast<const float4 *>(src);
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j)
+            if (st[j]) *reinterpret_cast<float *>(reinterpret_cast<char *>(src + j) + delta) = src[j];
+        }
+      }
+      SlabSyncItemDone(a.sync, item, H * 32, threadIdx.x == 0);
+    }
   }
+  if (SLAB) SlabSyncSignal(a.sync, H * 32, threadIdx.x == 0);
 }
 
-// 1 where a boundary cell of the two grids differs (bitwise), else untouched
+// 1 where a boundary cell of the two grids differs (bitwise), else untouched.  Local view of a
+// z-slab: the x and y faces of the interior planes [zlo, zhi), and the z faces this rank holds
+// (local planes zf_lo / zf_hi, -1 when they are on another rank).
 __global__ void HimenoFacesDifferKernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
-                                        int nx, int ny, int nz, int *flag) {
-  const long nxy = (long)nx * ny, nxz = (long)nx * nz, nyz = (long)ny * nz;
-  const long total = 2 * (nxy + nxz + nyz);
+                                        int nx, int ny, int zlo, int zhi, int zf_lo, int zf_hi, int *flag) {
+  const long nxy = (long)nx * ny;
+  const long ring = 2L * nx + 2L * ny;          // boundary cells of one plane's rim (corners twice)
+  const long rim = (long)(zhi - zlo) * ring;
+  const long total = rim + 2 * nxy;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long)gridDim.x * blockDim.x) {
-    long r = i;
     int x, y, z;
-    if (r < 2 * nxy) {
-      z = (r >= nxy) ? nz - 1 : 0;
-      r %= nxy;
-      y = (int)(r / nx);
-      x = (int)(r % nx);
-    } else if ((r -= 2 * nxy) < 2 * nxz) {
-      y = (r >= nxz) ? ny - 1 : 0;
-      r %= nxz;
-      z = (int)(r / nx);
-      x = (int)(r % nx);
+    if (i < rim) {
+      z = zlo + (int)(i / ring);
+      const long r = i % ring;
+      if (r < 2L * nx) {
+        y = (r >= nx) ? ny - 1 : 0;
+        x = (int)(r % nx);
+      } else {
+        const long q = r - 2L * nx;
+        x = (q >= ny) ? nx - 1 : 0;
+        y = (int)(q % ny);
+      }
     } else {
-      r -= 2 * nxz;
-      x = (r >= nyz) ? nx - 1 : 0;
-      r %= nyz;
-      z = (int)(r / ny);
-      y = (int)(r % ny);
+      const long r = i - rim;
+      z = (r >= nxy) ? zf_hi : zf_lo;
+      if (z < 0) continue;
+      y = (int)((r % nxy) / nx);
+      x = (int)(r % nx);
     }
     const size_t off = ((size_t)z * ny + y) * nx + x;
     if (a[off] != b[off]) *flag = 1;
@@ -361,7 +397,7 @@ HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
   for (int i = 2; i < ng; ++i)
     if (d0.grids[i] != d1.grids[i]) { *why = "the sweeps use different coefficient grids"; return nullptr; }
   if (d0.scalars[0] != d1.scalars[0]) { *why = "the sweeps use different omega"; return nullptr; }
-  if (rt->world() > 1) { *why = "fused Himeno passes run on one GPU only"; return nullptr; }
+  const bool multi = rt->world() > 1;
   Grid *g[15];
   for (int i = 0; i < ng; ++i) {
     g[i] = Grid::FromHandle(d0.grids[i]);
@@ -372,9 +408,26 @@ HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
   // neither p grid may double as a coefficient (or residual) grid
   for (int i = 2; i < ng; ++i)
     if (g[i] == g[0] || g[i] == g[1]) { *why = "a p grid is also a coefficient grid"; return nullptr; }
-  const int nx = g[0]->dim[0], ny = g[0]->dim[1], nz = g[0]->dim[2];
+  sweep::SlabSync sync{};
+  if (multi) {
+    // a fused pass consumes two halo planes per side and delivers two; every rank must take the
+    // same decision, so only group-wide quantities enter it
+    for (int i = 0; i < 14; ++i)
+      if (!g[i]->decomposed || g[i]->halo < 2 || g[i]->halo != g[0]->halo || g[i]->z_off != g[0]->z_off ||
+          g[i]->nz_loc != g[0]->nz_loc) {
+        *why = "z-slabs need two halo planes (option halo>=2) and identical cuts"; return nullptr;
+      }
+    if (g[0]->dim[2] / rt->world() < 4) { *why = "z-slabs thinner than four planes"; return nullptr; }
+    if (!o.halo_push || !rt->FillSlabSync(&sync)) {
+      *why = "needs the in-kernel halo exchange (halo_push=1, sync_mode=2)"; return nullptr;
+    }
+  }
+  const int nx = g[0]->dim[0], ny = g[0]->dim[1];
+  const int gnz = g[0]->dim[2];       // global planes
+  const int nz = g[0]->ldim[2];       // planes of this rank's allocation (halo planes included)
+  const int halo = g[0]->halo;
   if (nx % 4 != 0) { *why = "x extent must be a multiple of 4"; return nullptr; }
-  if (nx < 8 || ny < 3 || nz < 3) { *why = "grid too small"; return nullptr; }
+  if (nx < 8 || ny < 3 || gnz < 3) { *why = "grid too small"; return nullptr; }
   for (int s = 0; s < 2; ++s) {
     const __PSDomain &dom = s ? d1.dom : d0.dom;
     for (int i = 0; i < 3; ++i)
@@ -384,7 +437,7 @@ HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
   }
   constexpr int H = 12;
   HimenoPairPlan *p = new HimenoPairPlan();
-  p->fn = (const void *)HimenoPairKernel<H>;
+  p->fn = multi ? (const void *)HimenoPairKernel<H, true> : (const void *)HimenoPairKernel<H, false>;
   p->smem = HpGeom<H>::SMEM;
   p->block = H * 32;
   p->g[0] = g[0];
@@ -412,7 +465,11 @@ HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
     if (ntx > kHpMaxXTiles) { *why = "rows wider than 32 x tiles"; delete p; return nullptr; }
   }
   const int nty = CeilDiv(ny - 2, H - 2);
-  const int nzd = nz - 2;
+  // planes this rank writes: the global interior [1, gnz-1) cut to its slab, in local indices
+  const int dz0 = std::max(1, g[0]->z_off) - g[0]->z_off + halo;
+  const int dz1 = std::min(gnz - 1, g[0]->z_off + g[0]->nz_loc) - g[0]->z_off + halo;
+  const int nzd = dz1 - dz0;
+  if (nzd < 1) { *why = "a rank without interior planes"; delete p; return nullptr; }
   int zc = o.himeno_pair_zc;
   if (zc <= 0) {
     // every chunk re-reads 4 planes and recomputes 2 first-sweep planes; items run in waves
@@ -437,7 +494,8 @@ HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
     HimenoPairArgs &a = p->args[dir];
     // descriptor grid order: p0,p1,a0..a3,b0..b2,c0..c2,bnd,wrk1[,gosa]
     for (int i = 0; i < 12; ++i) a.coef[i] = (const float *)g[2 + i]->members[0].dev;
-    a.out = (float *)g[1 - dir]->members[0].dev;
+    Grid *go = g[1 - dir];
+    a.out = (float *)go->members[0].dev;
     a.omega = (float)d0.scalars[0];
     a.nx = nx; a.ny = ny; a.nz = nz;
     a.nty = nty; a.ntx = ntx; a.nzc = nzc; a.zc = zc;
@@ -447,33 +505,63 @@ HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
       a.txe[t] = std::min((t + 1) * seg, nx);
       a.tx0[t] = ntx == 1 ? 0 : std::max(0, std::min(a.txs[t] - 4, nx - w));
     }
-    a.dz0 = 1;
-    a.dz1 = nz - 1;
+    a.dz0 = dz0;
+    a.dz1 = dz1;
     a.pf = std::max(0, std::min(o.himeno_pair_pf, 8));
+    a.zface_lo = g[0]->LocalInterior(0);
+    a.zface_hi = g[0]->LocalInterior(gnz - 1);
+    a.push_lo_z = a.push_hi_z = -(1 << 30);
+    a.push_lo_delta = a.push_hi_delta = 0;
+    a.sync = sync;
+    if (multi) {
+      sweep::SlabSyncSetBoundary(&a.sync, o.early_signal != 0, nzd, zc, nzc, nty * ntx, 2);
+      const MemberLayout &ml = go->members[0];
+      const size_t plane = (size_t)go->plane_elms;
+      // lower neighbour's two upper halo planes <- my first two interior planes; upper neighbour's
+      // two lower halo planes (the ones next to its interior) <- my last two (planes holding a
+      // global z face are never written, so never forwarded: the kernel forwards what it stored)
+      a.push_lo_z = halo;
+      a.push_hi_z = halo + go->nz_loc - 2;
+      const float *to_lo = (const float *)ml.peer_lo + (size_t)(go->halo + go->lo_nz_loc) * plane;
+      const float *to_hi = (const float *)ml.peer_hi + (size_t)(go->halo - 2) * plane;
+      a.push_lo_delta = (const char *)to_lo - (const char *)(a.out + (size_t)a.push_lo_z * plane);
+      a.push_hi_delta = (const char *)to_hi - (const char *)(a.out + (size_t)a.push_hi_z * plane);
+    }
   }
   p->grid = std::min(p->args[0].nitems, slots);
   return p;
 }
 
 // true when the boundary cells of the pair's two grids are bit-equal (a fused pass takes the
-// intermediate field's boundary from the grid it reads).  Synchronises the stream.
+// intermediate field's boundary from the grid it reads) -- on every rank's share of them: the
+// decision is group-wide.  Synchronises the stream (and, multi-GPU, the ranks).
 bool HimenoPairFacesEqual(Runtime *rt, HimenoPairPlan *p) {
   DeviceBuffer &scr = rt->small_scratch(sizeof(int));
   int *flag = (int *)scr.get();
   PSB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), rt->stream));
   const HimenoPairArgs &a = p->args[0];
+  const Grid *g = p->g[0];
   HimenoFacesDifferKernel<<<rt->sm_count * 2, 256, 0, rt->stream>>>(
       (const uint32_t *)p->g[0]->members[0].dev, (const uint32_t *)p->g[1]->members[0].dev, a.nx, a.ny,
-      a.nz, flag);
+      g->halo, g->halo + g->nz_loc, a.zface_lo, a.zface_hi, flag);
   PSB_CUDA(cudaGetLastError());
   rt->stats.kernel_launches++;
   int differ = 0;
   PSB_CUDA(cudaMemcpyAsync(&differ, flag, sizeof(int), cudaMemcpyDeviceToHost, rt->stream));
   PSB_CUDA(cudaStreamSynchronize(rt->stream));
+  if (rt->world() > 1) {
+    std::vector<int> all(rt->world());
+    rt->comm->AllGather(&differ, all.data(), sizeof(int));
+    for (int v : all) differ |= v;
+  }
   return differ == 0;
 }
 
 void LaunchHimenoPair(Runtime *rt, HimenoPairPlan *p, int dir) {
+  if (rt->world() > 1) {
+    p->args[dir].sync.wait_epoch = rt->sweep_epoch;
+    p->args[dir].sync.signal_epoch = rt->sweep_epoch + 1;
+  }
   void *args[2] = {&p->tmap[dir], &p->args[dir]};
   PSB_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(p->block), args, p->smem, rt->stream));
 }

@@ -468,8 +468,18 @@ extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200St
     if (hpair && HimenoPairFacesEqual(rt, hpair)) {
       first_unfused = __PSB200FusedPassCount(iter);
       for (int s = 0; s < 2; ++s) Grid::FromHandle(descs[0].grids[s])->NoteEmit(descs[0].dom);
+      const bool multi = rt->world() > 1;
+      if (multi) {
+        // as for the 7-point pair: single sweeps keep only the halo plane next to the interior
+        // current, a fused pass reads two
+        rt->WaitNeighbours(rt->sweep_epoch);
+        rt->PushAllHalos(*Grid::FromHandle(descs[0].grids[0]));
+        ++rt->sweep_epoch;
+        rt->SignalNeighbours(rt->sweep_epoch);
+      }
       for (int i = 0; i < first_unfused; ++i) {
         LaunchHimenoPair(rt, hpair, i & 1);
+        if (multi) ++rt->sweep_epoch;
         rt->stats.kernel_launches++;
         rt->stats.fused_pairs++;
       }

@@ -138,6 +138,29 @@ def case_himeno():
         assert abs(b[2] - exact) <= 8e-6 * abs(exact), (b[2], exact)
 
 
+def case_himeno_pair():
+    """Fused two-sweep Himeno passes on z-slabs (two halo planes per side, forwarded by the
+    kernel): both p grids and the residual grid bit-identical to the oracle's sweep-by-sweep run."""
+    from physis_b200 import api
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    envopt = os.environ.get("PHYSIS_B200_OPTIONS", "")
+    in_kernel_exchange = "halo_push=0" not in envopt and "sync_mode=0" not in envopt and "sync_mode=1" not in envopt
+    for dims, nn in [((64, 32, 32), 8), ((128, 20, 13), 6), ((256, 30, 40), 10), ((136, 17, 33), 6)]:
+        seen = {}
+        for gosa in (False, True):
+            a = H.run_himeno(H.oracle_port(), dims, nn, gosa=gosa, seed=11)
+            b = H.run_himeno(H.b200_programs(), dims, nn, gosa=gosa, seed=11,
+                             before_finalize=lambda: seen.update(n=int(api.stats().fused_pairs)))
+            want = ((nn // 2 - 1) & ~1) if (world == 1 or (dims[2] // world >= 4 and in_kernel_exchange)) else 0
+            assert seen["n"] == want, (dims, seen, want)
+            check(f"himeno pair p0 {dims}", a[0], b[0], np.uint32)
+            check(f"himeno pair p1 {dims}", a[1], b[1], np.uint32)
+            if gosa:
+                check(f"himeno pair ss^2 {dims}", a[3], b[3], np.uint32)
+                exact = float(np.sum(a[3].astype(np.float64)))
+                assert abs(b[2] - exact) <= 8e-6 * abs(exact), (b[2], exact)
+
+
 def case_pstag():
     for (nx, ny, nz), count in [((64, 16, 8), 4), ((128, 32, 11), 3)]:
         u, kap = H.pstag_inputs(nx, ny, nz)
@@ -213,7 +236,7 @@ def case_golden_all():
         assert G.sha(G.stdout_of(n, got)) == G.GOLD[n]["sha256"], n
 
 
-CASES = {"golden": case_golden, "golden_all": case_golden_all, "pair_tail": case_pair_tail, "diffusion": case_diffusion, "pair": case_pair, "himeno": case_himeno, "pstag": case_pstag, "api": case_api}
+CASES = {"himeno_pair": case_himeno_pair, "golden": case_golden, "golden_all": case_golden_all, "pair_tail": case_pair_tail, "diffusion": case_diffusion, "pair": case_pair, "himeno": case_himeno, "pstag": case_pstag, "api": case_api}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

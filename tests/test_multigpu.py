@@ -60,7 +60,7 @@ def _run(world, cases, options=""):
 @pytest.mark.parametrize("options", ["halo_push=1", "halo_push=0", "halo_push=1,sync_mode=1",
                                      "halo_push=1,sync_mode=0", "halo_push=0,sync_mode=0"])
 def test_two_gpus_match_oracle(options):
-    _run(2, ["diffusion", "pair", "himeno", "pstag", "api"], options)
+    _run(2, ["diffusion", "pair", "himeno", "himeno_pair", "pstag", "api"], options)
 
 
 def test_two_gpus_reference_system_tests():
@@ -68,7 +68,7 @@ def test_two_gpus_reference_system_tests():
 
 
 def test_four_gpus_match_oracle():
-    _run(4, ["diffusion", "pair", "himeno", "pstag", "api"], "halo_push=1")
+    _run(4, ["diffusion", "pair", "himeno", "himeno_pair", "pstag", "api"], "halo_push=1")
 
 
 def test_three_gpus_uneven_slabs():
@@ -76,7 +76,7 @@ def test_three_gpus_uneven_slabs():
 
 
 def test_three_gpus_fused_pairs_uneven_slabs():
-    _run(3, ["pair", "diffusion"], "halo_push=1")
+    _run(3, ["pair", "himeno_pair", "diffusion"], "halo_push=1")
 
 
 def test_two_ranks_early_signal_with_one_plane_tail_chunk():
@@ -87,7 +87,7 @@ def test_two_ranks_early_signal_with_one_plane_tail_chunk():
 
 
 def test_eight_ranks_match_oracle():
-    _run(8, ["diffusion", "pair", "himeno", "pstag", "api"], "halo_push=1")
+    _run(8, ["diffusion", "pair", "himeno", "himeno_pair", "pstag", "api"], "halo_push=1")
 
 
 def test_two_ranks_full_reference_system_test_suite():
