@@ -113,17 +113,23 @@ Grid *GridSpace::Create(const __PSGridTypeInfo *ti, int num_dims, const int *dim
   const int last = num_dims - 1;
   g->plane_elms = g->num_elms / (dim[last] > 0 ? dim[last] : 1);
   g->nz_loc = dim[last];
+  // (computed from group-wide quantities, so every rank agrees)
+  int thinnest = dim[last];
   if (rt->world() > 1 && num_dims == 3) {
-    g->decomposed = true;
-    // halo width: the configured one (default 2, what the fused two-sweep pass needs), but never
-    // wider than the thinnest slab of this grid -- thin grids keep working with a one-plane halo
-    // (single sweeps only).  Computed from group-wide quantities, so every rank agrees.
-    int thinnest = dim[last];
     for (int r = 0; r < rt->world(); ++r) {
       int o_, l_;
       PartitionGridZ(dim[last], rt->domain_dims[last], rt->world(), r, &o_, &l_);
       thinnest = std::min(thinnest, l_);
     }
+  }
+  // A 3-D grid with fewer planes than some rank's share needs (e.g. the N x N x 1 grid of the
+  // reference's test_09, read at z = 0 from every plane of a full grid) is replicated like a 2-D
+  // one: every rank holds all of it.
+  if (rt->world() > 1 && num_dims == 3 && thinnest >= 1) {
+    g->decomposed = true;
+    // halo width: the configured one (default 2, what the fused two-sweep pass needs), but never
+    // wider than the thinnest slab of this grid -- thin grids keep working with a one-plane halo
+    // (single sweeps only).
     g->halo = std::max(1, std::min(rt->opt.halo, thinnest));
     int lo_off;
     PartitionGridZ(dim[last], rt->domain_dims[last], rt->world(), rt->rank(), &g->z_off, &g->nz_loc);

@@ -236,7 +236,21 @@ def case_golden_all():
         assert G.sha(G.stdout_of(n, got)) == G.GOLD[n]["sha256"], n
 
 
-CASES = {"himeno_pair": case_himeno_pair, "golden": case_golden, "golden_all": case_golden_all, "pair_tail": case_pair_tail, "diffusion": case_diffusion, "pair": case_pair, "himeno": case_himeno, "pstag": case_pstag, "api": case_api}
+def case_selfcheck():
+    """The reference system tests without a twin on z-slabs: each program's own check must pass and
+    the bytes must equal the REFERENCE target's (test_reduction-3d-prod within its own tolerance)."""
+    import test_selfcheck_suite as S
+    for n in sorted(S.SUITE):
+        want = S.run(H.oracle_port(), n)
+        got = S.run(H.b200_programs(), n)
+        if n == "test_reduction-3d-prod":
+            w, g = float(want.view(np.float32)[0]), float(got.view(np.float32)[0])
+            assert abs(w - g) <= 1e-5 * w, n
+        else:
+            assert got.tobytes() == want.tobytes(), n
+
+
+CASES = {"selfcheck": case_selfcheck, "himeno_pair": case_himeno_pair, "golden": case_golden, "golden_all": case_golden_all, "pair_tail": case_pair_tail, "diffusion": case_diffusion, "pair": case_pair, "himeno": case_himeno, "pstag": case_pstag, "api": case_api}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

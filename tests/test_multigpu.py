@@ -93,7 +93,7 @@ def test_eight_ranks_match_oracle():
 def test_two_ranks_full_reference_system_test_suite():
     # every reference system test with an expected-output twin, incl. kernels that wrap
     # periodically in z across the rank ring and user types with array members
-    _run(2, ["golden_all"], "halo=2")
+    _run(2, ["golden_all", "selfcheck"], "halo=2")
 
 
 def test_single_process_group_of_one():
