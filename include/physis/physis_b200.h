@@ -346,11 +346,20 @@ typedef struct {
   uint64_t halo_wait_ns_max;      /* longest single wait */
   uint64_t halo_wait_ctas;        /* CTAs that waited (boundary work items only) */
   uint64_t halo_wait_launches;    /* sweeps that took part */
+  /* option autotune=1 (cf. the reference's AUTO_TUNING trial iterations, include/physis/runtime.h:32-52,
+   * translator/configuration.cc:27-57): kernel forms timed on a run's own first iterations, and
+   * runs that then used a form other than the defaults */
+  uint64_t autotune_trials;
+  uint64_t autotuned_runs;
 } __PSB200Stats;
 void __PSB200GetStats(__PSB200Stats *out);
 void __PSB200ResetStats(void);
 /* Runtime knobs (tile shape etc.) for tuning runs: "key=value". Returns 0 on success. */
 int __PSB200SetOption(const char *key_value);
+/* What the tuner (option autotune=1) last settled on: "<option overrides | defaults>: <ms> per
+ * iteration (defaults <ms>; <n> forms tried)", "" before any tuning.  The string lives until
+ * the next tuned run. */
+const char *__PSB200LastTuning(void);
 const char *__PSB200Version(void);
 /* ---- multi-GPU (one process per GPU, SPMD) ------------ */
 /* Rank / size of the process group PSInit joined (RANK, WORLD_SIZE, LOCAL_RANK,

@@ -56,7 +56,8 @@ class Stats(C.Structure):
                 ("fused_pairs_timed", C.c_uint64), ("fused_pair_ms", C.c_double),
                 ("reduces_from_partials", C.c_uint64), ("plan_cache_hits", C.c_uint64),
                 ("halo_wait_ns_sum", C.c_uint64), ("halo_wait_ns_max", C.c_uint64),
-                ("halo_wait_ctas", C.c_uint64), ("halo_wait_launches", C.c_uint64)]
+                ("halo_wait_ctas", C.c_uint64), ("halo_wait_launches", C.c_uint64),
+                ("autotune_trials", C.c_uint64), ("autotuned_runs", C.c_uint64)]
 
 
 # every extern "C" symbol include/physis/physis_b200.h declares
@@ -67,7 +68,7 @@ EXPORTED_SYMBOLS = [
     "PSGridFree", "__PSReduceGridFloat", "__PSReduceGridDouble", "__PSReduceGridInt",
     "__PSReduceGridLong", "__PSB200StencilRun", "__PSB200FusedPassCount", "__PSB200GetStream", "__PSB200Synchronize",
     "__PSB200TimerStart", "__PSB200TimerStopMs", "__PSB200GetStats", "__PSB200ResetStats",
-    "__PSB200SetOption", "__PSB200Version", "__PSB200HostAlloc", "__PSB200HostFree", "__ps_trace",
+    "__PSB200SetOption", "__PSB200LastTuning", "__PSB200Version", "__PSB200HostAlloc", "__PSB200HostFree", "__ps_trace",
     "__PSB200Rank", "__PSB200WorldSize", "__PSB200GridLocalSize", "__PSB200GridCopyinLocal",
     "__PSB200GridCopyoutLocal", "__PSB200Partition", "__PSB200GroupSelfTest",
 ]
@@ -109,6 +110,7 @@ def rt():
     lib.__PSB200SetOption.argtypes = [C.c_char_p]
     lib.__PSB200SetOption.restype = C.c_int
     lib.__PSB200Version.restype = C.c_char_p
+    lib.__PSB200LastTuning.restype = C.c_char_p
     lib.__PSB200HostAlloc.argtypes = [C.c_size_t]
     lib.__PSB200HostAlloc.restype = C.c_void_p
     lib.__PSB200HostFree.argtypes = [C.c_void_p]
@@ -230,6 +232,11 @@ def stencil_run(iters, descs):
 def set_option(kv):
     if rt().__PSB200SetOption(kv.encode()) != 0:
         raise ValueError(f"unknown physis_b200 option {kv!r}")
+
+
+def last_tuning():
+    """What option autotune=1 last settled on (``__PSB200LastTuning``)."""
+    return rt().__PSB200LastTuning().decode()
 
 
 def stats():

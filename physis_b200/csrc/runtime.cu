@@ -338,6 +338,7 @@ void Runtime::Destroy() {
   if (g_rt->stream) cudaStreamSynchronize(g_rt->stream);
   if (g_rt->comm && g_rt->world() > 1) g_rt->comm->Barrier();  // nobody still writes my halos
   ClearPlanCache();
+  ClearTuning();
   g_rt->gs.Clear();
   g_rt->ShutdownGroup();
   delete g_rt;
@@ -494,8 +495,24 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "plan_cache") o->plan_cache = (int)val;
   else if (k == "halo_profile") o->halo_profile = (int)val;
   else if (k == "debug_slab") o->debug_slab = (int)val;
+  else if (k == "autotune") o->autotune = (int)val;
   else return -1;
   return 0;
+}
+
+int ParseOptionList(Options *o, const std::string &s, bool warn) {
+  int bad = 0;
+  size_t pos = 0;
+  while (pos < s.size()) {
+    size_t c = s.find(',', pos);
+    if (c == std::string::npos) c = s.size();
+    if (c > pos && ParseKV(o, s.substr(pos, c - pos)) != 0) {
+      ++bad;
+      if (warn) fprintf(stderr, "[physis-b200] ignoring unknown option '%s'\n", s.substr(pos, c - pos).c_str());
+    }
+    pos = c + 1;
+  }
+  return bad;
 }
 
 }  // namespace physis_b200
@@ -516,18 +533,7 @@ void PSInit(int *argc, char ***argv, int grid_num_dims, ...) {
   va_end(vl);
   Runtime::Create(argc, argv);
   for (int i = 0; i < PS_MAX_DIM; ++i) Runtime::Get()->domain_dims[i] = dd[i];
-  if (const char *env = getenv("PHYSIS_B200_OPTIONS")) {
-    std::string s(env);
-    size_t pos = 0;
-    while (pos < s.size()) {
-      size_t c = s.find(',', pos);
-      if (c == std::string::npos) c = s.size();
-      if (ParseKV(&Runtime::Get()->opt, s.substr(pos, c - pos)) != 0)
-        fprintf(stderr, "[physis-b200] ignoring unknown option '%s'\n",
-                s.substr(pos, c - pos).c_str());
-      pos = c + 1;
-    }
-  }
+  if (const char *env = getenv("PHYSIS_B200_OPTIONS")) ParseOptionList(&Runtime::Get()->opt, env, true);
 }
 
 void PSFinalize(void) { Runtime::Destroy(); }
@@ -897,6 +903,7 @@ void __PSB200ResetStats(void) {
 }
 int __PSB200SetOption(const char *kv) {
   ClearPlanCache();  // plans bake option-dependent choices in
+  ClearTuning();     // ... and so do the tuner's picks
   return ParseKV(&Runtime::Get()->opt, kv);
 }
 const char *__PSB200Version(void) { return "physis-b200 0.1 (sm_100a)"; }

@@ -201,7 +201,12 @@ struct Options {
   int debug_slab = 0;    // timing experiments (WRONG results): bit 0 no halo stores, bit 1 no neighbour ordering
   int halo_profile = 0;  // 1: sweeps record how long their CTAs wait for the ring neighbours
   int reduce_fuse = 1;   // PSReduce(PS_SUM) folds the partial sums the producing sweep left (himeno.cu)
+  int autotune = 0;      // 1: the first long PSStencilRun of a shape times the kernel forms that can run it
+                         //    on its own first iterations and keeps the fastest (stencil_run.cu)
 };
+
+// "k=v,k=v" onto *o; returns how many entries were not understood
+int ParseOptionList(Options *o, const std::string &list, bool warn);
 
 class Runtime {
  public:
@@ -308,5 +313,6 @@ const char *SweepName(const SweepPlan *plan);
 // prepared plans hold device addresses and option-dependent choices: dropped whenever a grid
 // is freed or an option changes
 void ClearPlanCache();
+void ClearTuning();
 
 }  // namespace physis_b200

@@ -88,6 +88,10 @@ struct PlanCache {
   uint64_t hits = 0, misses = 0;
 };
 PlanCache g_plans;
+// the tuner prepares plans under option overrides: they are cached beside the default ones
+std::string g_plan_tag;
+// ... and asks whether a form can run a shape at all, which must not end the program
+bool g_soft_fail = false;
 
 template <typename T>
 void KeyAdd(std::string *k, const T &v) { k->append(reinterpret_cast<const char *>(&v), sizeof(T)); }
@@ -107,6 +111,7 @@ std::string DescKey(const __PSB200StencilDesc &d) {
   for (int i = 0; i < d.num_scalars; ++i) KeyAdd(&k, d.scalars[i]);
   KeyAdd(&k, d.written_mask);
   KeyAdd(&k, d.z_reach);
+  k += g_plan_tag;
   return k;
 }
 
@@ -127,7 +132,7 @@ void ClearPlanCache() {
 }
 
 static SweepPlan *GetSweepPlan(Runtime *rt, const __PSB200StencilDesc &d) {
-  if (d.kind == PSB200_KIND_GENERIC || !rt->opt.plan_cache) return PrepareSweep(rt, d);
+  if (d.kind == PSB200_KIND_GENERIC || !rt->opt.plan_cache || g_soft_fail) return PrepareSweep(rt, d);
   const std::string key = DescKey(d);
   auto it = g_plans.sweeps.find(key);
   if (it != g_plans.sweeps.end()) {
@@ -337,6 +342,10 @@ SweepPlan *PrepareSweep(Runtime *rt, const __PSB200StencilDesc &d_in) {
     }
     return p;
   }
+  if (g_soft_fail) {
+    delete p;
+    return nullptr;
+  }
   fprintf(stderr, "[physis-b200] sweep '%s' (%s) cannot run: %s, and the program carries no "
                   "generic launch stub. There is no CPU fallback.\n",
           p->name.c_str(), KindName(d_in.kind), why.c_str());
@@ -397,33 +406,24 @@ using namespace physis_b200;
 // stays unfused, so the second grid ends up holding the second-newest field.
 extern "C" int __PSB200FusedPassCount(int iter) { return iter >= 3 ? ((iter - 1) & ~1) : 0; }
 
-extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200StencilDesc *descs) {
-  Runtime *rt = Runtime::Get();
-  // every rank has finished its earlier synchronous runtime calls that wrote grids from the
-  // host (copyin, PSGridSet, free): a neighbour's sweep must not deliver halo planes into a grid
-  // that is still being filled.  Between runs with nothing of the kind in between, the sweeps
-  // order themselves on the device, and the host stays out of it.
-  if (rt->world() > 1 && rt->group_dirty) {
-    rt->comm->Barrier();
-    rt->group_dirty = false;
-  }
+namespace {
+
+struct SegmentTiming {
+  bool timed = false;
+  cudaEvent_t emid = nullptr;  // recorded after the fused passes of the segment
+  int fused = 0;
+};
+
+// `iter` iterations of the stencils under the options in force.  `whole_fused` (a tuning trial
+// in the middle of a run; iter even): every iteration may run as a fused pass, the iterations
+// that follow put the second grid right.
+void RunSchedule(Runtime *rt, int iter, int num_stencils, const __PSB200StencilDesc *descs,
+                 bool whole_fused, SegmentTiming *tm) {
+  if (iter <= 0) return;
   std::vector<SweepPlan *> plans;
   plans.reserve(num_stencils);
-  std::string names;
-  for (int s = 0; s < num_stencils; ++s) {
-    plans.push_back(GetSweepPlan(rt, descs[s]));
-    if (s) names += ", ";
-    names += SweepName(plans.back());
-  }
-  const bool trace = (__ps_trace != nullptr);
-  const bool timed = trace || rt->opt.time_kernels;
-  if (trace) __PSTraceStencilPre(names.c_str());
-  cudaEvent_t e0 = nullptr, e1 = nullptr, emid = nullptr;
-  if (timed) {
-    PSB_CUDA(cudaEventCreate(&e0));
-    PSB_CUDA(cudaEventCreate(&e1));
-    PSB_CUDA(cudaEventRecord(e0, rt->stream));
-  }
+  for (int s = 0; s < num_stencils; ++s) plans.push_back(GetSweepPlan(rt, descs[s]));
+  const int fusable = whole_fused ? (iter & ~1) : __PSB200FusedPassCount(iter);
   // A ping-pong pair of whole-grid clamped 7-point sweeps (A -> B, B -> A) runs as fused
   // two-sweep passes (star7_pair.cu).  A pass reads one grid and writes the other, so an
   // even number of passes leaves the newest field in A; the last iteration(s) run
@@ -432,10 +432,10 @@ extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200St
   int first_unfused = 0;
   Star7PairPlan *pair = nullptr;
   bool pair_owned = false;
-  if (num_stencils == 2 && __PSB200FusedPassCount(iter) > 0 && plans[0]->star7 && plans[1]->star7) {
+  if (num_stencils == 2 && fusable > 0 && plans[0]->star7 && plans[1]->star7) {
     pair = GetPairPlan(rt, descs[0], descs[1], &pair_owned);
     if (pair) {
-      first_unfused = __PSB200FusedPassCount(iter);
+      first_unfused = fusable;
       const bool multi = rt->world() > 1;
       if (multi) {
         // single sweeps keep only the halo plane next to the interior current; a fused
@@ -452,10 +452,6 @@ extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200St
         rt->stats.kernel_launches++;
         rt->stats.fused_pairs++;
       }
-      if (timed) {
-        PSB_CUDA(cudaEventCreate(&emid));
-        PSB_CUDA(cudaEventRecord(emid, rt->stream));
-      }
     }
   }
   // The same for a ping-pong pair of Himeno sweeps (himeno_pair.cu): a pass takes the boundary
@@ -463,10 +459,10 @@ extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200St
   // cells of the two grids are bit-equal (one small comparison kernel per run).
   HimenoPairPlan *hpair = nullptr;
   bool hpair_owned = false;
-  if (!pair && num_stencils == 2 && __PSB200FusedPassCount(iter) > 0 && plans[0]->himeno && plans[1]->himeno) {
+  if (!pair && num_stencils == 2 && fusable > 0 && plans[0]->himeno && plans[1]->himeno) {
     hpair = GetHimenoPairPlan(rt, descs[0], descs[1], &hpair_owned);
     if (hpair && HimenoPairFacesEqual(rt, hpair)) {
-      first_unfused = __PSB200FusedPassCount(iter);
+      first_unfused = fusable;
       for (int s = 0; s < 2; ++s) Grid::FromHandle(descs[0].grids[s])->NoteEmit(descs[0].dom);
       const bool multi = rt->world() > 1;
       if (multi) {
@@ -483,26 +479,257 @@ extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200St
         rt->stats.kernel_launches++;
         rt->stats.fused_pairs++;
       }
-      if (timed) {
-        PSB_CUDA(cudaEventCreate(&emid));
-        PSB_CUDA(cudaEventRecord(emid, rt->stream));
-      }
     }
+  }
+  if (tm && tm->timed && first_unfused > 0) {
+    PSB_CUDA(cudaEventCreate(&tm->emid));
+    PSB_CUDA(cudaEventRecord(tm->emid, rt->stream));
+    tm->fused = first_unfused;
   }
   for (int i = first_unfused; i < iter; ++i)
     for (int s = 0; s < num_stencils; ++s) LaunchSweep(rt, plans[s]);
+  for (auto *p : plans) DestroySweep(p);
+  if (pair && pair_owned) DestroyStar7Pair(pair);
+  if (hpair && hpair_owned) DestroyHimenoPair(hpair);
+}
+
+// ---- tile-shape / schedule tuner ----------------------------------------------------------
+// The reference's auto-tuning compiles every CUDA_BLOCK_SIZE pattern into its own module and
+// lets the first iterations of PSStencilRun try them in random order before settling on the
+// fastest (translator/configuration.cc:27-57, reference_translator.cc:948,
+// cuda_translator.cc:35, include/physis/runtime.h:32-52).  Here the patterns are the forms the
+// hand-written kernels come in -- tile shapes, fused passes or single sweeps -- all of which
+// compute bit-identical results, so the trials are likewise real iterations of the run: with
+// option autotune=1 the first long run of a shape spends 6 iterations per form (2 to warm up,
+// 4 timed with CUDA events), keeps the fastest as a set of option overrides for that shape, and
+// every later run of the shape starts from there.  On a process group the ranks agree on the
+// slowest rank's time per form.
+struct TuneEntry {
+  std::string best;     // option overrides, "" = the defaults won
+  float best_ms = 0.0f, default_ms = 0.0f;  // per iteration
+  int forms = 0;
+};
+std::map<std::string, TuneEntry> g_tuned;
+std::string g_last_tuning;
+
+constexpr int kTuneWarm = 2, kTuneTimed = 4;
+
+// the shape of a run, without the identity of its grids
+std::string TuneKey(int num_stencils, const __PSB200StencilDesc *descs) {
+  std::string k;
+  KeyAdd(&k, num_stencils);
+  for (int s = 0; s < num_stencils; ++s) {
+    const __PSB200StencilDesc &d = descs[s];
+    KeyAdd(&k, d.kind);
+    KeyAdd(&k, d.elm_type);
+    KeyAdd(&k, d.dom);
+    KeyAdd(&k, d.num_grids);
+    for (int i = 0; i < d.num_grids; ++i) {
+      const Grid *g = Grid::FromHandle(d.grids[i]);
+      for (int a = 0; a < 3; ++a) KeyAdd(&k, g->dim[a]);
+      KeyAdd(&k, d.members[i]);
+    }
+    KeyAdd(&k, d.num_scalars);
+    for (int i = 0; i < d.num_scalars; ++i) KeyAdd(&k, d.scalars[i]);
+  }
+  return k;
+}
+
+std::vector<std::string> TuneForms(int num_stencils, const __PSB200StencilDesc *descs) {
+  std::vector<std::string> f;
+  f.push_back("");  // the defaults
+  bool all7 = true, allh = true, allp = true;
+  for (int s = 0; s < num_stencils; ++s) {
+    all7 = all7 && descs[s].kind == PSB200_KIND_DIFFUSION7_CLAMP;
+    allh = allh && (descs[s].kind == PSB200_KIND_HIMENO19 || descs[s].kind == PSB200_KIND_HIMENO19_GOSA);
+    allp = allp && descs[s].kind == PSB200_KIND_PERIODIC7_STAGGERED;
+  }
+  // z chunks of the fused passes: the planner's cost model (star7_pair.cu) against plain
+  // divisions of the planes this rank owns
+  auto chunk_forms = [&](const char *opt) {
+    const Grid *g = Grid::FromHandle(descs[0].grids[0]);
+    const int nz = g->decomposed ? g->nz_loc : g->dim[2];
+    int last = 0;
+    for (int d : {2, 4, 8, 16}) {
+      const int zc = (nz + d - 1) / d;
+      if (zc < 8 || zc == last) continue;
+      f.push_back(std::string(opt) + "=" + std::to_string(zc));
+      last = zc;
+    }
+  };
+  if (all7) {
+    const std::string single = num_stencils == 2 ? "star7_fuse=0," : "";
+    if (num_stencils == 2) {
+      chunk_forms("star7_pair_zc");
+      f.push_back("star7_fuse=0");
+    }
+    for (int v = 0; v < 6; ++v) f.push_back(single + "star7_variant=" + std::to_string(v));
+  } else if (allh) {
+    const std::string single = num_stencils == 2 ? "himeno_fuse=0," : "";
+    if (num_stencils == 2) {
+      chunk_forms("himeno_pair_zc");
+      f.push_back("himeno_fuse=0");
+    }
+    f.push_back(single + "himeno_by=7");
+  } else if (allp) {
+    f.push_back("pstag_variant=1");
+  } else {
+    f.clear();  // generated kernels: nothing to choose from
+  }
+  return f;
+}
+
+}  // namespace
+
+namespace physis_b200 {
+void ClearTuning() {
+  g_tuned.clear();
+  g_last_tuning.clear();
+}
+}
+
+namespace {
+
+// Runs the trials on the first iterations of this run; returns how many iterations they used.
+int TuneOnRun(Runtime *rt, const std::string &key, int iter, int num_stencils,
+              const __PSB200StencilDesc *descs) {
+  const std::vector<std::string> forms = TuneForms(num_stencils, descs);
+  const int per_form = kTuneWarm + kTuneTimed;
+  if (forms.size() < 2 || iter < (int)forms.size() * per_form + 1) return 0;
+  const Options saved = rt->opt;
+  struct Trial { std::string form; cudaEvent_t e0, e1; };
+  std::vector<Trial> trials;
+  int used = 0;
+  for (const std::string &form : forms) {
+    rt->opt = saved;
+    ParseOptionList(&rt->opt, form, false);
+    g_plan_tag = form;
+    // a form runs only if every rank's hand-written kernel takes the shape under it
+    int ok = 1;
+    if (!form.empty()) {
+      g_soft_fail = true;
+      for (int s = 0; s < num_stencils && ok; ++s) {
+        SweepPlan *p = GetSweepPlan(rt, descs[s]);
+        ok = (p != nullptr && (p->empty || p->star7 || p->himeno || p->pstag)) ? 1 : 0;
+        if (p) DestroySweep(p);
+      }
+      g_soft_fail = false;
+    }
+    if (rt->world() > 1) {
+      std::vector<int> all(rt->world());
+      rt->comm->AllGather(&ok, all.data(), sizeof(int));
+      for (int v : all) ok = ok && v;
+    }
+    if (!ok) continue;
+    Trial t{form, nullptr, nullptr};
+    PSB_CUDA(cudaEventCreate(&t.e0));
+    PSB_CUDA(cudaEventCreate(&t.e1));
+    RunSchedule(rt, kTuneWarm, num_stencils, descs, true, nullptr);
+    PSB_CUDA(cudaEventRecord(t.e0, rt->stream));
+    RunSchedule(rt, kTuneTimed, num_stencils, descs, true, nullptr);
+    PSB_CUDA(cudaEventRecord(t.e1, rt->stream));
+    trials.push_back(t);
+    used += per_form;
+    rt->stats.autotune_trials++;
+  }
+  rt->opt = saved;
+  g_plan_tag.clear();
+  std::vector<float> ms(trials.size(), 0.0f);
+  for (size_t i = 0; i < trials.size(); ++i) {
+    PSB_CUDA(cudaEventSynchronize(trials[i].e1));
+    PSB_CUDA(cudaEventElapsedTime(&ms[i], trials[i].e0, trials[i].e1));
+    ms[i] /= kTuneTimed;
+    PSB_CUDA(cudaEventDestroy(trials[i].e0));
+    PSB_CUDA(cudaEventDestroy(trials[i].e1));
+  }
+  if (rt->world() > 1 && !ms.empty()) {
+    // every rank ran the same forms; the slowest rank's time counts
+    std::vector<float> all(ms.size() * rt->world());
+    rt->comm->AllGather(ms.data(), all.data(), ms.size() * sizeof(float));
+    for (size_t i = 0; i < ms.size(); ++i)
+      for (int r = 0; r < rt->world(); ++r) ms[i] = std::max(ms[i], all[r * ms.size() + i]);
+  }
+  TuneEntry e;
+  e.forms = (int)trials.size();
+  size_t best = 0;
+  for (size_t i = 1; i < trials.size(); ++i)
+    if (ms[i] < ms[best] * 0.99f) best = i;  // the defaults keep ties
+  e.best = trials[best].form;
+  e.best_ms = ms[best];
+  e.default_ms = ms[0];
+  g_tuned[key] = e;
+  char buf[256];
+  snprintf(buf, sizeof buf, "%s%s: %.4f ms per iteration (defaults %.4f; %d forms tried)",
+           e.best.empty() ? "defaults" : e.best.c_str(), "", e.best_ms, e.default_ms, e.forms);
+  g_last_tuning = buf;
+  // the trial plans of the forms that lost are of no further use
+  ClearPlanCache();
+  return used;
+}
+
+}  // namespace
+
+extern "C" const char *__PSB200LastTuning(void) { return g_last_tuning.c_str(); }
+
+extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200StencilDesc *descs) {
+  Runtime *rt = Runtime::Get();
+  // every rank has finished its earlier synchronous runtime calls that wrote grids from the
+  // host (copyin, PSGridSet, free): a neighbour's sweep must not deliver halo planes into a grid
+  // that is still being filled.  Between runs with nothing of the kind in between, the sweeps
+  // order themselves on the device, and the host stays out of it.
+  if (rt->world() > 1 && rt->group_dirty) {
+    rt->comm->Barrier();
+    rt->group_dirty = false;
+  }
+  std::string names;
+  for (int s = 0; s < num_stencils; ++s) {
+    if (s) names += ", ";
+    names += descs[s].name ? descs[s].name : KindName(descs[s].kind);
+  }
+  const bool trace = (__ps_trace != nullptr);
+  SegmentTiming tm;
+  tm.timed = trace || rt->opt.time_kernels;
+  if (trace) __PSTraceStencilPre(names.c_str());
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (tm.timed) {
+    PSB_CUDA(cudaEventCreate(&e0));
+    PSB_CUDA(cudaEventCreate(&e1));
+    PSB_CUDA(cudaEventRecord(e0, rt->stream));
+  }
+  int done = 0;
+  const TuneEntry *tuned = nullptr;
+  if (rt->opt.autotune) {
+    const std::string key = TuneKey(num_stencils, descs);
+    auto it = g_tuned.find(key);
+    if (it == g_tuned.end()) {
+      done = TuneOnRun(rt, key, iter, num_stencils, descs);
+      it = g_tuned.find(key);
+    }
+    if (it != g_tuned.end()) tuned = &it->second;
+  }
+  if (tuned && !tuned->best.empty()) {
+    const Options saved = rt->opt;
+    ParseOptionList(&rt->opt, tuned->best, false);
+    g_plan_tag = tuned->best;
+    RunSchedule(rt, iter - done, num_stencils, descs, false, done ? nullptr : &tm);
+    rt->opt = saved;
+    g_plan_tag.clear();
+    rt->stats.autotuned_runs++;
+  } else {
+    RunSchedule(rt, iter - done, num_stencils, descs, false, done ? nullptr : &tm);
+  }
   PSB_CUDA(cudaGetLastError());
   float ms = 0.0f;
-  if (timed) {
+  if (tm.timed) {
     PSB_CUDA(cudaEventRecord(e1, rt->stream));
     PSB_CUDA(cudaEventSynchronize(e1));
     PSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    if (emid) {
+    if (tm.emid) {
       float pms = 0.0f;
-      PSB_CUDA(cudaEventElapsedTime(&pms, e0, emid));
+      PSB_CUDA(cudaEventElapsedTime(&pms, e0, tm.emid));
       rt->stats.fused_pair_ms += pms;
-      rt->stats.fused_pairs_timed += (uint64_t)first_unfused;
-      PSB_CUDA(cudaEventDestroy(emid));
+      rt->stats.fused_pairs_timed += (uint64_t)tm.fused;
+      PSB_CUDA(cudaEventDestroy(tm.emid));
     }
     PSB_CUDA(cudaEventDestroy(e0));
     PSB_CUDA(cudaEventDestroy(e1));
@@ -510,8 +737,5 @@ extern "C" float __PSB200StencilRun(int iter, int num_stencils, const __PSB200St
     rt->timed_launches += (uint64_t)iter * num_stencils;
   }
   if (trace) __PSTraceStencilPost(ms);
-  for (auto *p : plans) DestroySweep(p);
-  if (pair && pair_owned) DestroyStar7Pair(pair);
-  if (hpair && hpair_owned) DestroyHimenoPair(hpair);
   return trace ? ms : 0.0f;
 }

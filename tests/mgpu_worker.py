@@ -250,7 +250,39 @@ def case_selfcheck():
             assert got.tobytes() == want.tobytes(), n
 
 
-CASES = {"selfcheck": case_selfcheck, "himeno_pair": case_himeno_pair, "golden": case_golden, "golden_all": case_golden_all, "pair_tail": case_pair_tail, "diffusion": case_diffusion, "pair": case_pair, "himeno": case_himeno, "pstag": case_pstag, "api": case_api}
+def case_autotune():
+    """Option autotune=1 on z-slabs: the ranks try the same forms on the run's own first iterations
+    and agree on the slowest rank's times; the result stays the oracle's bits."""
+    from physis_b200 import api
+    co64 = np.array([0.11, 0.07, 0.13, 0.05, 0.17, 0.03, 0.44])
+    co = [float(np.float32(c)) for c in co64]
+    for shape in [(128, 32, 16), (512, 12, 24)]:
+        nx, ny, nz = shape
+        api.PSInit(["t"], 3, shape)
+        api.set_option("autotune=1")
+        a, b = api.Grid(shape, api.PS_FLOAT), api.Grid(shape, api.PS_FLOAT)
+        f0 = np.random.default_rng(nx).random(nx * ny * nz, dtype=np.float32)
+        a.copyin(f0)
+        dom = api.PSDomain3DNew(0, nx, 0, ny, 0, nz)
+        d0 = api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, dom, [a, b], co)
+        d1 = api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, dom, [b, a], co)
+        api.rt().__PSB200ResetStats()
+        api.stencil_run(60, [d0, d1])
+        assert int(api.stats().autotune_trials) >= 3
+        api.stencil_run(7, [d0, d1])
+        want = H.diffusion7_numpy(f0, shape, co64.astype(np.float32), 2 * 67)
+        check(f"autotune {shape}", want, a.copyout(), np.uint32)
+        api.PSFinalize()
+    dims, nn = (64, 20, 24), 40
+    os.environ["PHYSIS_B200_OPTIONS"] = "autotune=0"
+    ref = H.run_himeno(H.oracle_port(), dims, nn, seed=4)
+    os.environ["PHYSIS_B200_OPTIONS"] = "autotune=1"
+    got = H.run_himeno(H.b200_programs(), dims, nn, seed=4)
+    for i in (0, 1):
+        check(f"autotune himeno p{i}", ref[i], got[i], np.uint32)
+
+
+CASES = {"autotune": case_autotune, "selfcheck": case_selfcheck, "himeno_pair": case_himeno_pair, "golden": case_golden, "golden_all": case_golden_all, "pair_tail": case_pair_tail, "diffusion": case_diffusion, "pair": case_pair, "himeno": case_himeno, "pstag": case_pstag, "api": case_api}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

@@ -96,6 +96,12 @@ def test_two_ranks_full_reference_system_test_suite():
     _run(2, ["golden_all", "selfcheck"], "halo=2")
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_ranks_tune_on_their_own_iterations(world):
+    # option autotune=1: same forms tried on every rank, one decision for the group
+    _run(world, ["autotune"], "")
+
+
 def test_single_process_group_of_one():
     # WORLD_SIZE=1 through the same launcher path
     _run(1, ["diffusion", "pair", "api"], "")
