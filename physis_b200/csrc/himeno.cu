@@ -328,7 +328,9 @@ HimenoPlan *PrepareHimeno(Runtime *rt, const __PSB200StencilDesc &d, std::string
   // groups of four, so 7+1 (two CTAs per SM) and 15+1 fill the register file where
   // 8+1 strands three warps' worth.
   int TY = rt->opt.himeno_by;
-  if (TY != 7 && TY != 15) TY = 15;  // measured best (profiles/r1_tune_himeno_XL.csv); 7: two CTAs per SM
+  // measured (profiles/r1_tune_himeno_XL.csv, r2_experiments.txt): 15 rows best on XL, 7 rows (two
+  // CTAs per SM, twice the work items) on 512x256x256 and smaller
+  if (TY != 7 && TY != 15) TY = (double)nx * ny * (dom.local_max[2] - dom.local_min[2]) >= 1.0e8 ? 15 : 7;
   int stages = rt->opt.himeno_stages > 0 ? std::min(rt->opt.himeno_stages, kMaxStages) : 6;
   if (stages < 4) stages = 4;
   if (TY == 7) {

@@ -470,19 +470,39 @@ HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
   const int dz1 = std::min(gnz - 1, g[0]->z_off + g[0]->nz_loc) - g[0]->z_off + halo;
   const int nzd = dz1 - dz0;
   if (nzd < 1) { *why = "a rank without interior planes"; delete p; return nullptr; }
-  int zc = o.himeno_pair_zc;
-  if (zc <= 0) {
-    // every chunk re-reads 4 planes and recomputes 2 first-sweep planes; items run in waves
+  // every chunk re-reads 4 planes and recomputes 2 first-sweep planes; items run in waves
+  auto plan_zc = [&](int planes) {
+    int best_zc = planes;
     long best = -1;
-    for (int n = 1; n <= std::max(1, nzd / 4); ++n) {
-      const int c = CeilDiv(nzd, n);
-      const long waves = CeilDiv((long)nty * ntx * CeilDiv(nzd, c), slots);
+    for (int n = 1; n <= std::max(1, planes / 4); ++n) {
+      const int c = CeilDiv(planes, n);
+      const long waves = CeilDiv((long)nty * ntx * CeilDiv(planes, c), slots);
       const long cost = waves * (c + 3);
-      if (best < 0 || cost < best) { best = cost; zc = c; }
+      if (best < 0 || cost < best) { best = cost; best_zc = c; }
     }
-  }
+    return best_zc;
+  };
+  int zc = o.himeno_pair_zc > 0 ? o.himeno_pair_zc : plan_zc(nzd);
   zc = std::max(1, std::min(zc, nzd));
   const int nzc = CeilDiv(nzd, zc);
+  // Shapes the fused form wastes itself on run sweep by sweep (himeno_fuse=2 fuses regardless):
+  // measured (profiles/r2_experiments.txt) 256x128x128 -- three x tiles that use 96 of the tile's
+  // 128 columns, 117 work items for 148 SMs -- 92.9 GLUP/s fused against 115.5 sweep by sweep,
+  // while 128x64x64 (launch-bound: fewer launches win), 512x256x256 and 1024x512x512 are
+  // faster fused.  Judged on an even share of the planes, so that every rank of a group decides alike.
+  {
+    const int share = std::max(1, (gnz - 2) / rt->world());
+    const int szc = o.himeno_pair_zc > 0 ? std::min(o.himeno_pair_zc, share) : plan_zc(share);
+    const long items = (long)nty * ntx * CeilDiv(share, szc);
+    const double lanes = (double)nx / ((double)ntx * w);
+    const double fill = (double)items / (double)(CeilDiv(items, (long)slots) * slots);
+    const double cells = (double)nx * ny * share;
+    if (o.himeno_fuse == 1 && lanes * fill < 0.7 && cells > 1.5e6) {
+      *why = "too few or too narrow work items for the fused form";
+      delete p;
+      return nullptr;
+    }
+  }
   for (int dir = 0; dir < 2; ++dir) {
     int dimv[3] = {nx, ny, nz};
     int boxv[3] = {Geom<float>::BW, H + 2, 1};

@@ -177,6 +177,7 @@ struct Options {
   int himeno_by = 0, himeno_zc = 0, himeno_stages = 0, himeno_occ = 0, himeno_carveout = 0;
   int himeno_sthint = 0;    // bit 0 / bit 1: evict-first stores of p1 / of the residual grid
   int himeno_fuse = 1;      // 1: a ping-pong pair of interior Himeno sweeps runs as fused two-sweep passes
+                            //    where that pays, 2: wherever it can, 0: never
   int himeno_pair_zc = 0;   // z chunk of the fused Himeno kernel; 0 = automatic
   int himeno_pair_pf = 1;   // planes ahead the coefficient rows are prefetched into L2
   int pstag_push = 0;     // 1: the config-5 sweep stores its halo planes and orders itself in the kernel

@@ -568,9 +568,10 @@ std::vector<std::string> TuneForms(int num_stencils, const __PSB200StencilDesc *
     const std::string single = num_stencils == 2 ? "himeno_fuse=0," : "";
     if (num_stencils == 2) {
       chunk_forms("himeno_pair_zc");
-      f.push_back("himeno_fuse=0");
+      f.push_back("himeno_fuse=2");  // fused also where the planner would rather not
     }
     f.push_back(single + "himeno_by=7");
+    f.push_back(single + "himeno_by=15");
   } else if (allp) {
     f.push_back("pstag_variant=1");
   } else {

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Himeno XL timing under a list of option sets (tuning tool, GPU box only):
-EXP_CONFIGS="a=1+b=2|c=3" python tools/exp_himeno.py [XL|L] [nn]"""
+EXP_CONFIGS="a=1+b=2|c=3" EXP_MODES=sweeps,each python tools/exp_himeno.py [XL|L|M|S] [nn]"""
 import ctypes as C
 import os
 import sys
@@ -12,7 +12,7 @@ from physis_b200 import api
 
 size = sys.argv[1] if len(sys.argv) > 1 else "XL"
 nn = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-mi, mj, mk = (1024, 512, 512) if size == "XL" else (512, 256, 256)
+mi, mj, mk = {"XL": (1024, 512, 512), "L": (512, 256, 256), "M": (256, 128, 128), "S": (128, 64, 64)}[size]
 lib = physis_b200.load_programs()
 lib.himeno_init_local.argtypes = [C.c_int] * 3
 lib.himeno_sweeps_only.argtypes = [C.c_int, C.c_int]
@@ -26,7 +26,7 @@ for cfg in configs:
     for kv in cfg:
         api.set_option(kv)
     r = api.rt()
-    for mode in ("sweeps", "each"):
+    for mode in os.environ.get("EXP_MODES", "sweeps,each").split(","):
         run = (lambda: lib.himeno_sweeps_only(nn, 0)) if mode == "sweeps" else (lambda: lib.himeno_jacobi_gosa_each(nn))
         run()
         r.__PSB200Synchronize()
