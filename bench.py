@@ -325,9 +325,11 @@ def himeno_line(args, api, lib, world, dist):
         ms = api.rt().__PSB200TimerStopMs()
         _barrier(dist)
         ms = _max_over_ranks(dist, ms)
-        # 12 coefficient/source reads + p read + p write (himenobmtxpa_physis.c:418-432), + the
-        # 4-byte ss*ss emit; the reduction reads one fp64 per CTA, not the grid
-        bpl = 60 if with_gosa else 56
+        # 12 coefficient/source reads + p read + p write (himenobmtxpa_physis.c:418-432); with the
+        # residual, + the 4-byte ss*ss emit of the second sweep of every pair (the first one's would be
+        # overwritten before anything reads it, so that sweep runs in its plain form): 58 on
+        # average; the reduction reads one fp64 per CTA, not the grid
+        bpl = 58 if with_gosa else 56
         key = "with_residual" if with_gosa else "sweep_only"
         gbs = pts * nn * bpl / ms / 1e6
         out[key] = {"glups": pts * nn / ms / 1e6, "ms_per_sweep": ms / nn,

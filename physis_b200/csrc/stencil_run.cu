@@ -7,6 +7,7 @@
 #include "runtime.h"
 
 #include <algorithm>
+#include <cstring>
 #include <map>
 #include <string>
 #include <utility>
@@ -486,8 +487,41 @@ void RunSchedule(Runtime *rt, int iter, int num_stencils, const __PSB200StencilD
     PSB_CUDA(cudaEventRecord(tm->emid, rt->stream));
     tm->fused = first_unfused;
   }
+  // A residual-emitting Himeno sweep whose residual grid a later sweep of this run overwrites
+  // over the same domain (the second sweep of the ping-pong pair, or the next iteration) runs in
+  // its plain form: the emission would be dead (4 B per point written for nothing, and the
+  // per-CTA partial sums with it).  The grid ends up with the last sweep's values either way.
+  std::vector<SweepPlan *> lean(num_stencils, nullptr);
+  std::vector<char> dead_in_iter(num_stencils, 0), dead_before_next(num_stencils, 0);
+  if (rt->opt.reduce_fuse && first_unfused < iter) {
+    for (int s = 0; s < num_stencils; ++s) {
+      if (descs[s].kind != PSB200_KIND_HIMENO19_GOSA || !plans[s]->himeno || descs[s].num_grids < 15) continue;
+      for (int t = 0; t < num_stencils; ++t) {
+        const bool same = descs[t].kind == PSB200_KIND_HIMENO19_GOSA && plans[t]->himeno && descs[t].num_grids >= 15 &&
+                          descs[t].grids[14] == descs[s].grids[14] &&
+                          memcmp(&descs[t].dom, &descs[s].dom, sizeof(descs[s].dom)) == 0;
+        if (!same) continue;
+        if (t > s) dead_in_iter[s] = 1;
+        dead_before_next[s] = 1;  // (t == s: the sweep itself, one iteration later)
+      }
+      if (!dead_in_iter[s] && !(dead_before_next[s] && iter - first_unfused > 1)) continue;
+      __PSB200StencilDesc twin = descs[s];
+      twin.kind = PSB200_KIND_HIMENO19;
+      twin.num_grids = 14;
+      lean[s] = GetSweepPlan(rt, twin);
+      if (!lean[s]->himeno) {
+        DestroySweep(lean[s]);
+        lean[s] = nullptr;
+      }
+    }
+  }
   for (int i = first_unfused; i < iter; ++i)
-    for (int s = 0; s < num_stencils; ++s) LaunchSweep(rt, plans[s]);
+    for (int s = 0; s < num_stencils; ++s) {
+      const bool dead = lean[s] && (dead_in_iter[s] || (dead_before_next[s] && i + 1 < iter));
+      LaunchSweep(rt, dead ? lean[s] : plans[s]);
+    }
+  for (auto *p : lean)
+    if (p) DestroySweep(p);
   for (auto *p : plans) DestroySweep(p);
   if (pair && pair_owned) DestroyStar7Pair(pair);
   if (hpair && hpair_owned) DestroyHimenoPair(hpair);
