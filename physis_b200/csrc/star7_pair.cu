@@ -548,6 +548,27 @@ Star7PairPlan *PrepareStar7Pair(Runtime *rt, const __PSB200StencilDesc &d0,
       seg = CeilDiv(CeilDiv(nx, ntx), vec) * vec;
       if (seg + 2 * vec <= w) break;
     }
+    if (ntx <= kPairMaxXTiles && o.star7_pair_variant < 0 && o.star7_pair_zc <= 0) {
+      // 20-row tiles (15 warps) or 16-row tiles of the same width (12 warps; a plane step takes
+      // 0.85 of the time instead of 0.8: measured, profiles/r2_experiments.txt): whichever
+      // tiling wastes less of the last wave of work items -- on 1024x1024x128 (an eighth of
+      // 1024^3) 222 tiles x 2 chunks fill three waves exactly where 171 tiles x 6 chunks leave
+      // 7 % of the seventh idle and pay for three times the chunk overlap
+      auto plan_cost = [&](int vi, double step) {
+        const int hh = kPairVariants[vi].nwy * kPairVariants[vi].ry;
+        const long tiles = (long)CeilDiv(ny, hh - 2) * ntx;
+        double best = -1.0;
+        for (int nzc = 1; nzc <= std::max(1, nz / 4); ++nzc) {
+          const int c = CeilDiv(nz, nzc);
+          const long waves = CeilDiv(tiles * CeilDiv(nz, c), (long)rt->sm_count);
+          const double cost = (double)waves * (c + 3) * step;
+          if (best < 0 || cost < best) best = cost;
+        }
+        return best;
+      };
+      static_assert(kPairWideVariant == 4, "the 16-row twin of the wide variant is variant 1");
+      if (plan_cost(1, 0.85) < plan_cost(kPairWideVariant, 1.0)) variant = 1;
+    }
     if (ntx > kPairMaxXTiles) { *why = "rows wider than 16 x tiles of the fused kernel"; return nullptr; }
   }
   if (nz < 2 || ny < 2) { *why = "grid too thin"; return nullptr; }

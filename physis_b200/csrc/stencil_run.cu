@@ -580,14 +580,14 @@ std::vector<std::string> TuneForms(int num_stencils, const __PSB200StencilDesc *
   }
   // z chunks of the fused passes: the planner's cost model (star7_pair.cu) against plain
   // divisions of the planes this rank owns
-  auto chunk_forms = [&](const char *opt) {
+  auto chunk_forms = [&](const std::string &opt) {
     const Grid *g = Grid::FromHandle(descs[0].grids[0]);
     const int nz = g->decomposed ? g->nz_loc : g->dim[2];
     int last = 0;
     for (int d : {2, 4, 8, 16}) {
       const int zc = (nz + d - 1) / d;
       if (zc < 8 || zc == last) continue;
-      f.push_back(std::string(opt) + "=" + std::to_string(zc));
+      f.push_back(opt + "=" + std::to_string(zc));
       last = zc;
     }
   };
@@ -595,6 +595,12 @@ std::vector<std::string> TuneForms(int num_stencils, const __PSB200StencilDesc *
     const std::string single = num_stencils == 2 ? "star7_fuse=0," : "";
     if (num_stencils == 2) {
       chunk_forms("star7_pair_zc");
+      // rows cut into x tiles: the 16-row tile (fewer warps, more tiles) against the 20-row one
+      const Grid *g = Grid::FromHandle(descs[0].grids[0]);
+      if ((size_t)g->dim[0] * (g->type == PS_DOUBLE ? 8 : 4) > 2048) {
+        f.push_back("star7_pair_variant=1");
+        chunk_forms("star7_pair_variant=1,star7_pair_zc");
+      }
       f.push_back("star7_fuse=0");
     }
     for (int v = 0; v < 6; ++v) f.push_back(single + "star7_variant=" + std::to_string(v));

@@ -223,19 +223,24 @@ __device__ __forceinline__ void SlabSyncWait(const SlabSync &s) {
 }
 
 // Called by every consumer thread of a CTA after it has finished work item `item`: the last
-// of the boundary items to finish publishes the sweep's number to both neighbours.
+// of the boundary items to finish publishes the sweep's number to both neighbours.  A CTA's
+// boundary items are the first of its sequence (item, item + gridDim.x, ...): it reports them all
+// at once after the last of them -- one barrier and one fence per CTA, not per item (a fence
+// after megabytes of stores costs microseconds).
 __device__ __forceinline__ void SlabSyncItemDone(const SlabSync &s, int item, int nthreads, bool leader) {
   if (!s.done || item >= s.boundary_items) return;
+  if (item + (int)gridDim.x < s.boundary_items) return;  // more boundary items of this CTA follow
   // every consumer's stores (incl. the peer stores) precede the barrier; the leader's
   // system-scope fence after it then orders all of them before the counter and the flags
   // (fence cumulativity -- the pattern of a grid-wide barrier: bar.sync, one thread fences and
-  // signals).  One fence per CTA instead of one per thread: a fence waits for the acknowledgement
-  // of the thread's outstanding NVLink stores.
+  // signals).  (A GPU-scope fence here with a single system-scope one in the publishing CTA
+  // measured the same: profiles/r2_experiments.txt.)
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
   if (leader) {
+    const unsigned mine = 1u + (unsigned)(item / (int)gridDim.x);  // boundary items this CTA ran
     __threadfence_system();
-    const unsigned prev = atomicAdd(s.done, 1u);
-    if (prev == (unsigned)s.boundary_items - 1u) {
+    const unsigned prev = atomicAdd(s.done, mine);
+    if (prev + mine == (unsigned)s.boundary_items) {
       *s.done = 0;           // next launch starts from zero (stream order)
       __threadfence_system();
       StReleaseSys(s.to_lo, s.signal_epoch);

@@ -57,10 +57,18 @@ def run_himeno(dims, nn, tune):
 
 
 if __name__ == "__main__":
-    for dims in [(128, 64, 64), (256, 128, 128), (512, 256, 256), (1024, 512, 512)]:
+    for dims in [] if os.environ.get("EXP_SHAPES") else [(128, 64, 64), (256, 128, 128), (512, 256, 256), (1024, 512, 512)]:
         g0, _ = run_himeno(dims, 100, 0)
         g1, what = run_himeno(dims, 100, 1)
         print(f"himeno {dims}: defaults {g0:.1f} GLUP/s, autotune {g1:.1f} GLUP/s  [{what}]", flush=True)
+    shapes = os.environ.get("EXP_SHAPES")
+    if shapes:
+        for sh in shapes.split("|"):
+            shape = tuple(int(v) for v in sh.split("x"))
+            g0, _ = run(shape, 400, 0)
+            g1, what = run(shape, 400, 1)
+            print(f"{shape}: defaults {g0:.1f} GLUP/s, autotune {g1:.1f} GLUP/s  [{what}]", flush=True)
+        sys.exit(0)
     for shape in [(64, 64, 64), (128, 128, 128), (256, 256, 256), (384, 384, 384), (512, 512, 512), (256, 512, 1024),
                   (640, 640, 640), (1024, 256, 256)]:
         g0, _ = run(shape, 1000, 0)
