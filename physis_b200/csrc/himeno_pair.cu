@@ -68,6 +68,7 @@ struct HimenoPairArgs {
   int tx0[kHpMaxXTiles], txs[kHpMaxXTiles], txe[kHpMaxXTiles];
   int dz0, dz1;  // planes written (local indices): the global interior [1, n-1) cut to this rank's slab
   int pf;        // coefficient prefetch distance in planes
+  int pf_tensor; // 1: by tensor-map prefetch of the tile's box, 0: by bulk prefetches per row
   // z-slab view (multi-GPU; on one GPU the faces are planes 0 and nz-1 and nothing is pushed): local
   // planes holding the global z faces (-1 when they are elsewhere), whose cells no sweep updates;
   // the slab's first two / last two planes are also stored into the ring neighbours' halo planes
@@ -81,6 +82,18 @@ struct HimenoPairArgs {
 __device__ __forceinline__ void PrefetchL2(const void *p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+
+// Two ways to pull the coefficient rows of the next plane towards L2 (HimenoPairArgs::pf_tensor):
+//  - a bulk prefetch per row and array from 12 lanes of every warp: a serialised loop per lane
+//    (a fifth of the kernel's instructions), but every warp fetches its own row exactly when it
+//    is about to need it;
+//  - a tensor-map prefetch of the tile's box of an array (128 columns x H rows x 1 plane): 12
+//    instructions of one thread per plane.
+// Measured (profiles/r2_experiments.txt): XL 152.1 / 147.1 GLUP/s (none: 144.7-146.2), L 127.8 /
+// 133.4-135.9 (none: 127.0-127.8); the planner picks by plane size (PrepareHimenoPair).
+struct alignas(64) HpCoefMaps {
+  CUtensorMap m[12];
+};
 
 // The update of this thread's four cells from three planes of a ring (pb / pc / pt point at the
 // thread's own vector in the planes below / at / above): vectors of the rows above and below
@@ -151,7 +164,8 @@ struct HpGeom {
 // SLAB: the z-slab form (halo planes forwarded to the ring neighbours, ordering with them).
 template <int H, bool SLAB>
 __global__ void __launch_bounds__(H * 32, 1)
-HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ HimenoPairArgs a) {
+HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ HpCoefMaps cm,
+                 const __grid_constant__ HimenoPairArgs a) {
   using G = Geom<float>;
   using PG = HpGeom<H>;
   constexpr int VEC = 4;
@@ -214,8 +228,9 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     // lane); lanes beyond the grid's last column compute on zeros and store nothing
     const bool ld_row = row_in_grid && !row_bnd;
     const bool ld_ok = (x < a.nx);
-    // offset of this thread's vector inside a plane of the coefficient arrays / of `out`
-    const size_t gp = (size_t)y * a.nx + x;
+    // offset of this thread's vector inside a plane of the coefficient arrays / of `out`; lanes
+    // beyond the last column load the row's last vector instead (their values reach nothing stored)
+    const size_t gp = (size_t)y * a.nx + (ld_ok ? x : a.nx - VEC);
 
     // every thread is done with both rings of the previous item
     __syncthreads();
@@ -228,8 +243,14 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         }
       }
     }
-    // pull the coefficient rows of the first planes towards L2 (one array per lane)
-    if (lane < 12 && ld_row) {
+    // pull the coefficient rows of the first planes towards L2
+    if (a.pf_tensor) {
+      if (issuer) {
+        for (int m = max(zb - 1, 0); m < min(zb - 1 + a.pf, a.nz); ++m)
+#pragma unroll
+          for (int c = 0; c < 12; ++c) tma::prefetch_3d(&cm.m[c], xt0, ty * (H - 2), m);
+      }
+    } else if (lane < 12 && ld_row) {
       const uint32_t bytes = (uint32_t)min(G::TXB, a.nx - xt0) * 4u;
       for (int m = max(zb - 1, 0); m < min(zb - 1 + a.pf, a.nz); ++m)
         PrefetchL2(a.coef[lane] + (size_t)m * plane_elems + (size_t)y * a.nx + xt0, bytes);
@@ -243,8 +264,9 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     par ^= 1u << 1;
 
     float4 hold[12];  // coefficients of plane k (loaded as plane m of the previous step)
+    float4 q[12];     // coefficients of plane m (rows / planes no sweep updates load nothing)
 #pragma unroll
-    for (int c = 0; c < 12; ++c) hold[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < 12; ++c) hold[c] = q[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = kfirst; k < ze; ++k) {
       const int m = k + 1;  // plane whose first-sweep values this step computes
       const int slot_c = (slot_b + 1 == kHpInSlots) ? 0 : slot_b + 1;
@@ -252,19 +274,25 @@ HimenoPairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       const bool plane_upd = (m != a.zface_lo) && (m != a.zface_hi) && (m >= 0) && (m < a.nz);
       const size_t gm = (size_t)m * plane_elems + gp;
       // ---- first sweep: s1(m) from p(m-1), p(m), p(m+1) ---------------------------------
-      float4 q[12];
-#pragma unroll
-      for (int c = 0; c < 12; ++c) q[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       const bool compute1 = ld_row && plane_upd;
       if (compute1) {
 #pragma unroll
-        for (int c = 0; c < 12; ++c)
-          if (ld_ok) q[c] = __ldg(reinterpret_cast<const float4 *>(a.coef[c] + gm));
-        // and the row of plane m + pf towards L2
+        for (int c = 0; c < 12; ++c) q[c] = __ldg(reinterpret_cast<const float4 *>(a.coef[c] + gm));
+      }
+      // and the tile's rows of plane m + pf towards L2
+      {
         const int mp = m + a.pf;
-        if (a.pf > 0 && lane < 12 && mp < a.nz && mp <= ze)
-          PrefetchL2(a.coef[lane] + (size_t)mp * plane_elems + (size_t)y * a.nx + xt0,
-                     (uint32_t)min(G::TXB, a.nx - xt0) * 4u);
+        if (a.pf > 0 && mp < a.nz && mp <= ze) {
+          if (a.pf_tensor) {
+            if (issuer) {
+#pragma unroll
+              for (int c = 0; c < 12; ++c) tma::prefetch_3d(&cm.m[c], xt0, ty * (H - 2), mp);
+            }
+          } else if (compute1 && lane < 12) {
+            PrefetchL2(a.coef[lane] + (size_t)mp * plane_elems + (size_t)y * a.nx + xt0,
+                       (uint32_t)min(G::TXB, a.nx - xt0) * 4u);
+          }
+        }
       }
       tma::mbar_wait(&full[slot_t], (par >> slot_t) & 1u);
       par ^= 1u << slot_t;
@@ -374,6 +402,7 @@ struct HimenoPairPlan {
   size_t smem = 0;
   const void *fn = nullptr;
   CUtensorMap tmap[2];  // direction 0 reads the first grid, direction 1 the second
+  HpCoefMaps cmaps;     // the coefficient arrays (prefetch boxes)
   HimenoPairArgs args[2];
   Grid *g[2] = {nullptr, nullptr};
 };
@@ -503,6 +532,15 @@ HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
       return nullptr;
     }
   }
+  for (int i = 0; i < 12; ++i) {
+    int dimv[3] = {nx, ny, nz};
+    int boxv[3] = {std::min(Geom<float>::TXB, nx), std::min(H, ny), 1};
+    if (!EncodeTensorMap3D(&p->cmaps.m[i], TmaElem::F32, g[2 + i]->members[0].dev, dimv, boxv)) {
+      *why = "grid shape violates a TMA constraint";
+      delete p;
+      return nullptr;
+    }
+  }
   for (int dir = 0; dir < 2; ++dir) {
     int dimv[3] = {nx, ny, nz};
     int boxv[3] = {Geom<float>::BW, H + 2, 1};
@@ -528,6 +566,11 @@ HimenoPairPlan *PrepareHimenoPair(Runtime *rt, const __PSB200StencilDesc &d0,
     a.dz0 = dz0;
     a.dz1 = dz1;
     a.pf = std::max(0, std::min(o.himeno_pair_pf, 8));
+    // automatic: per-row bulk prefetches once a plane of the 12 arrays is 20 MB or more (measured on
+    // eight shapes: they win on 1024x512x512 and 2048x256x256, 24 MB, by 3-4 %; the tensor form wins on
+    // everything from 128x64x64 to 640x512x256, 16 MB, by 1-10 %)
+    const bool big_planes = (size_t)nx * ny * sizeof(float) * 12 >= (size_t)20 << 20;
+    a.pf_tensor = o.himeno_pair_pfmode == 2 ? 1 : o.himeno_pair_pfmode == 1 ? 0 : (big_planes ? 0 : 1);
     a.zface_lo = g[0]->LocalInterior(0);
     a.zface_hi = g[0]->LocalInterior(gnz - 1);
     a.push_lo_z = a.push_hi_z = -(1 << 30);
@@ -582,7 +625,7 @@ void LaunchHimenoPair(Runtime *rt, HimenoPairPlan *p, int dir) {
     p->args[dir].sync.wait_epoch = rt->sweep_epoch;
     p->args[dir].sync.signal_epoch = rt->sweep_epoch + 1;
   }
-  void *args[2] = {&p->tmap[dir], &p->args[dir]};
+  void *args[3] = {&p->tmap[dir], &p->cmaps, &p->args[dir]};
   PSB_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(p->block), args, p->smem, rt->stream));
 }
 

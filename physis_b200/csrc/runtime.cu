@@ -477,6 +477,7 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "himeno_sthint") o->himeno_sthint = (int)val;
   else if (k == "himeno_pair_zc") o->himeno_pair_zc = (int)val;
   else if (k == "himeno_pair_pf") o->himeno_pair_pf = (int)val;
+  else if (k == "himeno_pair_pfmode") o->himeno_pair_pfmode = (int)val;
   else if (k == "pstag_variant") o->pstag_variant = (int)val;
   else if (k == "pstag_stages") o->pstag_stages = (int)val;
   else if (k == "pstag_occ") o->pstag_occ = (int)val;

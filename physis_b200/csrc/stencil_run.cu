@@ -609,6 +609,8 @@ std::vector<std::string> TuneForms(int num_stencils, const __PSB200StencilDesc *
     if (num_stencils == 2) {
       chunk_forms("himeno_pair_zc");
       f.push_back("himeno_fuse=2");  // fused also where the planner would rather not
+      f.push_back("himeno_pair_pfmode=1");  // coefficient prefetch by rows / by tensor-map boxes
+      f.push_back("himeno_pair_pfmode=2");
     }
     f.push_back(single + "himeno_by=7");
     f.push_back(single + "himeno_by=15");

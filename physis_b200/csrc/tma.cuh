@@ -82,6 +82,13 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
 
+// 3-D tiled prefetch global -> L2 of the box at (c0, c1, c2): one instruction of one thread for
+// the whole box, no shared memory, no completion to wait for.
+__device__ __forceinline__ void prefetch_3d(const CUtensorMap *m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // 3-D tiled load global -> shared; completion is signalled on `bar` as
 // transaction bytes.  Out-of-bounds box elements are zero-filled.
 __device__ __forceinline__ void load_3d(void *smem_dst, const CUtensorMap *m, uint64_t *bar,

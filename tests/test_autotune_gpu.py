@@ -59,13 +59,13 @@ def test_diffusion_tuned_on_its_own_iterations(shape):
 @pytest.mark.parametrize("gosa", [False, True])
 def test_himeno_tuned(monkeypatch, gosa):
     from physis_b200 import api
-    dims, nn = (136, 21, 14), 60
+    dims, nn = (136, 21, 14), 80
     a = H.run_himeno(H.oracle_port(), dims, nn, gosa=gosa, seed=11, omega=0.1)
     monkeypatch.setenv("PHYSIS_B200_OPTIONS", "autotune=1")
     seen = {}
     b = H.run_himeno(H.b200_programs(), dims, nn, gosa=gosa, seed=11, omega=0.1,
                      before_finalize=lambda: seen.update(n=int(api.stats().autotune_trials), s=api.last_tuning()))
-    assert seen["n"] == 4, seen   # the defaults, fused regardless, single sweeps with 7- and 15-row tiles
+    assert seen["n"] == 6, seen   # the defaults, fused regardless, two prefetch forms, single sweeps with 7- and 15-row tiles
     for i in (0, 1, 3):
         assert np.array_equal(a[i].view(np.uint32), b[i].view(np.uint32))
     if gosa:

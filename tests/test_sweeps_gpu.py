@@ -160,6 +160,9 @@ def test_reduce_partials_are_dropped_when_the_grid_changes():
 @pytest.mark.parametrize("dims,nn,opts", [
     ((64, 32, 32), 6, ()), ((128, 40, 21), 8, ()), ((136, 17, 9), 6, ()), ((256, 33, 19), 10, ("himeno_pair_zc=5",)),
     ((1024, 20, 13), 6, ()), ((520, 45, 12), 8, ("himeno_pair_zc=3",)), ((8, 5, 4), 6, ()), ((64, 16, 3), 6, ()),
+    # both ways of pulling the coefficient rows towards L2: bulk prefetches per row, tensor-map boxes
+    ((1024, 20, 13), 6, ("himeno_pair_pfmode=1",)), ((1024, 20, 13), 6, ("himeno_pair_pfmode=2", "himeno_pair_pf=2")),
+    ((136, 29, 11), 8, ("himeno_pair_pfmode=1", "himeno_pair_pf=3")), ((136, 29, 11), 8, ("himeno_pair_pfmode=2",)),
 ])
 def test_himeno_fused_two_sweep_passes_match_oracle(dims, nn, opts):
     """A ping-pong run of nn/2 >= 3 iterations executes fused two-sweep passes (himeno_pair.cu):

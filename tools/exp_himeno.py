@@ -12,7 +12,7 @@ from physis_b200 import api
 
 size = sys.argv[1] if len(sys.argv) > 1 else "XL"
 nn = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-mi, mj, mk = {"XL": (1024, 512, 512), "L": (512, 256, 256), "M": (256, 128, 128), "S": (128, 64, 64)}[size]
+mi, mj, mk = {"XL": (1024, 512, 512), "L": (512, 256, 256), "M": (256, 128, 128), "S": (128, 64, 64)}.get(size) or tuple(int(v) for v in size.split("x"))
 lib = physis_b200.load_programs()
 lib.himeno_init_local.argtypes = [C.c_int] * 3
 lib.himeno_sweeps_only.argtypes = [C.c_int, C.c_int]
