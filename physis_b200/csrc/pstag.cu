@@ -480,11 +480,13 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
   }
   a.push_lo_z = a.push_hi_z = -1;
   a.sync = SlabSync{};
-  // The exchange of this sweep is copy-based by default (peer copies of the two boundary planes
-  // and stream-ordered flags after the kernel): measured on 2 GPUs at 512^3 per GPU it costs 7 %
-  // of a sweep against 13-15 % for the in-kernel form (option pstag_push=1) -- with 1024 small
-  // tiles per slab every work item carries a fence and a counter update, and short boundary
-  // chunks that would confine them pay the ring's fill latency 2048 times.
+  // The exchange of this sweep: in the kernel (halo planes stored to the ring neighbours by the
+  // CTAs that compute them, ordering by SlabSync), with the sweep's number published when the
+  // whole sweep is done (pstag_push=1, the default), the same with the boundary chunks first
+  // and an early signal (pstag_push=2), or copy-based (pstag_push=0: peer copies of the two
+  // boundary planes and stream-ordered flags after the kernel).  Measured on 2 GPUs at 512^3 per
+  // GPU (profiles/r2_experiments.txt): 0.570 / 0.584 / 0.583 ms per sweep -- with 1024 small tiles
+  // per slab and four CTAs per SM, boundary-first ordering costs more than the overlap returns.
   if (rt->opt.pstag_push &&
       SlabPushTargets(rt, *u, wr, (void **)&a.push_lo, (void **)&a.push_hi, sizeof(double))) {
     a.push_lo_z = u->halo;
@@ -492,7 +494,8 @@ PstagPlan *PreparePstag(Runtime *rt, const __PSB200StencilDesc &d, std::string *
     p->pushes = true;
     if (rt->FillSlabSync(&a.sync)) {
       p->syncs = true;
-      SlabSyncPlanEnds(&a.sync, rt->opt.early_signal != 0, nzd, &a.zc, &a.nzc, a.ntx * a.nty, 1, rt->opt.slab_zbl);
+      SlabSyncPlanEnds(&a.sync, rt->opt.early_signal != 0 && rt->opt.pstag_push == 2, nzd, &a.zc, &a.nzc,
+                       a.ntx * a.nty, 1, rt->opt.slab_zbl);
       a.nitems = tiles * a.nzc;
       p->grid = std::min(a.nitems, slots);
     }

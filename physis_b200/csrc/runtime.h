@@ -181,7 +181,8 @@ struct Options {
   int himeno_pair_zc = 0;   // z chunk of the fused Himeno kernel; 0 = automatic
   int himeno_pair_pf = 1;   // planes ahead the coefficient rows are prefetched into L2
   int himeno_pair_pfmode = 0;  // ... 1: by bulk prefetches per row, 2: by tensor-map prefetch of the tile, 0: automatic
-  int pstag_push = 0;     // 1: the config-5 sweep stores its halo planes and orders itself in the kernel
+  int pstag_push = 1;     // the config-5 sweep's exchange: 1 in the kernel, number published at the end of the
+                          // sweep; 2 in the kernel with boundary chunks first and an early signal; 0 copy-based
   int pstag_variant = 0 /* index into pstag.cu's tile shapes */, pstag_stages = 0, pstag_occ = 0;
   int time_kernels = 0;        // per-family CUDA-event timing (for bench roofline)
   size_t stage_chunk = 64u << 20;  // pinned staging chunk for pageable copies

@@ -63,6 +63,14 @@ def test_two_gpus_match_oracle(options):
     _run(2, ["diffusion", "pair", "himeno", "himeno_pair", "pstag", "api"], options)
 
 
+@pytest.mark.parametrize("options", ["pstag_push=0", "pstag_push=2", "pstag_push=2,slab_zbl=0"])
+def test_config5_exchange_forms(options):
+    # config 5's halo exchange: copy-based, in the kernel with the early signal (default: in the
+    # kernel, number published at the end of the sweep)
+    _run(2, ["pstag"], options)
+    _run(3, ["pstag"], options)
+
+
 def test_two_gpus_reference_system_tests():
     _run(2, ["golden"], "halo=2")
 
