@@ -497,6 +497,7 @@ static int ParseKV(Options *o, const std::string &kv) {
   else if (k == "halo_profile") o->halo_profile = (int)val;
   else if (k == "debug_slab") o->debug_slab = (int)val;
   else if (k == "autotune") o->autotune = (int)val;
+  else if (k == "pdl") o->pdl = (int)val;
   else return -1;
   return 0;
 }

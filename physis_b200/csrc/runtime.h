@@ -201,6 +201,7 @@ struct Options {
   int copyout_gather = 1;  // PSGridCopyout fills the whole host array on every rank
   int sync_timeout_s = 120;  // a neighbour silent for longer than this is a reported error
   int plan_cache = 1;    // keep prepared sweep plans across PSStencilRun calls
+  int pdl = 1;           // fused passes are launched as programmatic dependents of the pass before them
   int debug_slab = 0;    // timing experiments (WRONG results): bit 0 no halo stores, bit 1 no neighbour ordering
   int halo_profile = 0;  // 1: sweeps record how long their CTAs wait for the ring neighbours
   int reduce_fuse = 1;   // PSReduce(PS_SUM) folds the partial sums the producing sweep left (himeno.cu)

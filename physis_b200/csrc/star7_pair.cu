@@ -124,6 +124,11 @@ Star7PairKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     tma::fence_barrier_init();
     tma::prefetch_tensormap(&tmap);
   }
+  // Programmatic dependent launch (LaunchStar7Pair): the pass after this one may bring its CTAs
+  // onto SMs this pass has left and run the prologue above while this pass's last CTAs finish;
+  // nothing of the grids is touched before the pass before this one is complete and visible.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (SLAB) SlabSyncWait(a.sync);  // before any halo plane is read or any peer halo written
 
   const int bx = warp % NBX;
@@ -716,7 +721,22 @@ void LaunchStar7Pair(Runtime *rt, Star7PairPlan *p, int dir) {
   void *args[2];
   args[0] = &p->tmap[dir];
   args[1] = p->is_double ? (void *)&p->ad[dir] : (void *)&p->af[dir];
-  PSB_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(p->block), args, p->smem, rt->stream));
+  if (!rt->opt.pdl) {
+    PSB_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(p->block), args, p->smem, rt->stream));
+    return;
+  }
+  // consecutive passes: the next one is launched as a programmatic dependent of this one
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p->grid);
+  cfg.blockDim = dim3(p->block);
+  cfg.dynamicSmemBytes = p->smem;
+  cfg.stream = rt->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PSB_CUDA(cudaLaunchKernelExC(&cfg, p->fn, args));
 }
 
 void DestroyStar7Pair(Star7PairPlan *p) { delete p; }
