@@ -201,7 +201,7 @@ struct Options {
   int copyout_gather = 1;  // PSGridCopyout fills the whole host array on every rank
   int sync_timeout_s = 120;  // a neighbour silent for longer than this is a reported error
   int plan_cache = 1;    // keep prepared sweep plans across PSStencilRun calls
-  int pdl = 1;           // fused passes are launched as programmatic dependents of the pass before them
+  int pdl = 1;           // 7-point sweeps and fused passes are launched as programmatic dependents of the kernel before them
   int debug_slab = 0;    // timing experiments (WRONG results): bit 0 no halo stores, bit 1 no neighbour ordering
   int halo_profile = 0;  // 1: sweeps record how long their CTAs wait for the ring neighbours
   int reduce_fuse = 1;   // PSReduce(PS_SUM) folds the partial sums the producing sweep left (himeno.cu)
@@ -318,5 +318,26 @@ const char *SweepName(const SweepPlan *plan);
 // is freed or an option changes
 void ClearPlanCache();
 void ClearTuning();
+
+// Launch of a sweep kernel that begins with `griddepcontrol.wait` (and ONLY of such a kernel):
+// as a programmatic dependent of the kernel before it in the stream, so that its CTAs may run
+// their prologue on SMs that kernel has already left (option pdl).
+inline void LaunchSweepKernel(Runtime *rt, const void *fn, int grid, int block, void **args, size_t smem) {
+  if (!rt->opt.pdl) {
+    PSB_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, rt->stream));
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = rt->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PSB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+}
 
 }  // namespace physis_b200

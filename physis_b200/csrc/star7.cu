@@ -111,6 +111,10 @@ Star7KernelV2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     }
     tma::fence_barrier_init();
   }
+  // programmatic dependent launch (LaunchSweepKernel): nothing of the grids is touched before
+  // the kernel before this one is complete and visible
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   SlabSyncWait(a.sync);
   __syncthreads();
 
@@ -487,7 +491,7 @@ void LaunchStar7(Runtime *rt, Star7Plan *p) {
   void *args[2];
   args[0] = &p->tmap;
   args[1] = p->is_double ? (void *)&p->ad : (void *)&p->af;
-  PSB_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(p->block), args, p->smem, rt->stream));
+  LaunchSweepKernel(rt, p->fn, p->grid, p->block, args, p->smem);
 }
 
 void DestroyStar7(Star7Plan *p) { delete p; }

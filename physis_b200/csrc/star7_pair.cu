@@ -721,22 +721,7 @@ void LaunchStar7Pair(Runtime *rt, Star7PairPlan *p, int dir) {
   void *args[2];
   args[0] = &p->tmap[dir];
   args[1] = p->is_double ? (void *)&p->ad[dir] : (void *)&p->af[dir];
-  if (!rt->opt.pdl) {
-    PSB_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(p->block), args, p->smem, rt->stream));
-    return;
-  }
-  // consecutive passes: the next one is launched as a programmatic dependent of this one
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(p->grid);
-  cfg.blockDim = dim3(p->block);
-  cfg.dynamicSmemBytes = p->smem;
-  cfg.stream = rt->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  PSB_CUDA(cudaLaunchKernelExC(&cfg, p->fn, args));
+  LaunchSweepKernel(rt, p->fn, p->grid, p->block, args, p->smem);
 }
 
 void DestroyStar7Pair(Star7PairPlan *p) { delete p; }
