@@ -148,3 +148,14 @@ def test_fused_schedule_leaves_grids_as_the_reference_schedule_does():
         if it > 0:
             assert level == {"A": 2 * it, "B": 2 * it - 1}, (it, passes, level)
     assert lib.__PSB200FusedPassCount(500) == 498
+
+
+def test_every_runtime_option_is_documented():
+    """INTEGRATION.md §6 lists every key `PHYSIS_B200_OPTIONS` / `__PSB200SetOption` understands."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    keys = re.findall(r'k == "([a-z0-9_]+)"', open(os.path.join(root, "physis_b200", "csrc", "runtime.cu")).read())
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    assert len(keys) > 30
+    missing = [k for k in keys if f"`{k}`" not in doc]
+    assert not missing, missing
