@@ -16,6 +16,7 @@ run racecheck_himeno_pair racecheck 600 tests/test_sweeps_gpu.py -k "fused_two_s
 run synccheck_pair synccheck 300 tests/test_star7_pair_gpu.py -k "fp32_matches_oracle and (shape1 or shape4 or shape12)"
 run synccheck_himeno_pair synccheck 300 tests/test_sweeps_gpu.py -k "fused_two_sweep and (dims0 or dims2)"
 run memcheck_autotune memcheck 600 tests/test_autotune_gpu.py
+run initcheck_sweeps initcheck 600 tests/test_sweeps_gpu.py -k "(matches_oracle or fused_two_sweep or residual_reduced) and not variants"
 # two ranks on one GPU: the in-kernel neighbour ordering (named barriers, per-CTA reporting)
 timeout 500 compute-sanitizer --tool synccheck --target-processes all --error-exitcode 9 --print-limit 20 $PY tests/test_multigpu.py -k "tail_chunk or (tune_on_their_own_iterations and 2)" > $OUT/${R}_sanitize_synccheck_two_ranks.log 2>&1
 echo "rc=$?" >> $OUT/${R}_sanitize_synccheck_two_ranks.log
