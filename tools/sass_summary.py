@@ -2,8 +2,9 @@
 """Per-kernel SASS evidence from the built runtime library (no GPU needed):
 python tools/sass_summary.py > profiles/rN_sass_summary.txt
 Counts the mnemonics that show what the kernels are made of: UTMALDG (TMA tile loads), SYNCS
-(mbarrier), LDS/STS, SHFL, STG.E.128 (128-bit stores), FADD2 (packed adds), and FFMA / DFMA, whose
-absence is the bit-exactness argument (every multiply and add rounds separately)."""
+(mbarrier), LDS/STS, SHFL, STG.E.128 (128-bit stores), FADD2 (packed adds), UTMACCTL.PF / UBLKPF (tensor-map /
+bulk L2 prefetch), PREEXIT (programmatic dependent launch), and FFMA / DFMA, whose absence is the
+bit-exactness argument (every multiply and add rounds separately)."""
 import collections
 import os
 import re
@@ -28,13 +29,16 @@ for line in sass.splitlines():
         op = m.group(1)
         kernels[cur]["total"] += 1
         for key in ("UTMALDG", "SYNCS", "SHFL", "FADD2", "FFMA", "DFMA", "FMUL", "FADD", "DMUL", "DADD", "LDS", "STS",
-                    "LDG", "UBLKPF", "MEMBAR"):
+                    "LDG", "UBLKPF", "MEMBAR", "PREEXIT"):
             if op == key or op.startswith(key + "."):
                 kernels[cur][key] += 1
         if op.startswith("STG.E.128") or op.startswith("STG.E.EF.128"):
             kernels[cur]["STG.128"] += 1
+        if op.startswith("UTMACCTL.PF") or op.startswith("UTMAPF"):
+            kernels[cur]["TMAPF"] += 1
 print(f"library: {os.path.relpath(lib, ROOT)}   cubin architectures: {', '.join(arch)}   kernels: {len(kernels)}")
-cols = ["total", "UTMALDG", "SYNCS", "LDS", "STS", "SHFL", "LDG", "STG.128", "FMUL", "FADD", "FADD2", "DMUL", "DADD", "FFMA", "DFMA"]
+cols = ["total", "UTMALDG", "TMAPF", "UBLKPF", "PREEXIT", "SYNCS", "LDS", "STS", "SHFL", "LDG", "STG.128", "FMUL", "FADD", "FADD2", "DMUL",
+        "DADD", "FFMA", "DFMA"]
 print(f"{'kernel':78s} " + " ".join(f"{c:>7s}" for c in cols))
 tot_fma = 0
 for name, c in kernels.items():
