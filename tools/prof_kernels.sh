@@ -10,6 +10,8 @@ timeout 300 $NCU -k regex:Star7Pair -s 4 -c 1 -o $OUT/${R}_prof_pair $B --no-str
 timeout 300 $NCU -k regex:Star7Pair -s 4 -c 1 -o $OUT/${R}_prof_pair_slabform $B --no-strong --opt debug_slab=4 > $OUT/${R}_prof_pair_slabform.log 2>&1
 # x-tiled fused pass on 1024-wide rows (BASELINE config 4's grid on one GPU)
 timeout 300 $NCU --kernel-name-base demangled -k "regex:Star7PairKernel<float, \(int\)3" -s 2 -c 1 -o $OUT/${R}_prof_pair_xtile $B > $OUT/${R}_prof_pair_xtile.log 2>&1
+# single 7-point sweep (the tail of the schedule, and everything a program calling PSStencilRun(..., 1) runs)
+timeout 300 $NCU -k regex:Star7KernelV2 -s 2 -c 1 -o $OUT/${R}_prof_star7 $B --no-strong > $OUT/${R}_prof_star7.log 2>&1
 timeout 300 $NCU -k regex:HimenoPair -s 2 -c 1 -o $OUT/${R}_prof_himeno_pair $B --no-strong > $OUT/${R}_prof_himeno_pair.log 2>&1
 # residual form of the single Himeno sweep (the with_residual bench leg)
 timeout 300 $NCU --kernel-name-base demangled -k "regex:HimenoKernel<\(int\)15, \(bool\)1" -s 2 -c 1 -o $OUT/${R}_prof_himeno_gosa $B --no-strong > $OUT/${R}_prof_himeno_gosa.log 2>&1
