@@ -159,3 +159,34 @@ def test_every_runtime_option_is_documented():
     assert len(keys) > 30
     missing = [k for k in keys if f"`{k}`" not in doc]
     assert not missing, missing
+
+
+def test_kernels_carry_no_fused_multiply_add_and_are_sm100a_only():
+    """The bit-exactness argument, checked on the built library: every multiply and add of the
+    sweep kernels rounds separately (no FFMA / DFMA in any kernel's SASS), the sweep kernels move
+    their tiles with TMA (UTMALDG), and the only architecture in the library is sm_100a."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "physis_b200", "lib", "libphysis_rt_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    assert set(re.findall(r"arch = (sm_\w+)", sass)) == {"sm_100a"}
+    ops = {}
+    cur = None
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            ops[cur] = set()
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\w+\s+)?([A-Z0-9_]+)", line)
+        if m and cur:
+            ops[cur].add(m.group(1))
+    assert len(ops) > 50
+    # (HFMA2 does appear: the compiler's idiom for materialising a constant, not arithmetic on data)
+    fused = sorted(k for k, v in ops.items() if v & {"FFMA", "DFMA", "FFMA2"})
+    assert not fused, fused[:3]
+    for family in ("Star7KernelV2", "Star7PairKernel", "HimenoKernel", "HimenoPairKernel", "PstagKernel"):
+        ks = [k for k in ops if family in k]
+        assert ks and all("UTMALDG" in ops[k] for k in ks), family
