@@ -496,6 +496,13 @@ void RunSchedule(Runtime *rt, int iter, int num_stencils, const __PSB200StencilD
   if (rt->opt.reduce_fuse && first_unfused < iter) {
     for (int s = 0; s < num_stencils; ++s) {
       if (descs[s].kind != PSB200_KIND_HIMENO19_GOSA || !plans[s]->himeno || descs[s].num_grids < 15) continue;
+      // ... unless some stencil of the run uses that grid in any other role (it may read it)
+      bool other_use = false;
+      for (int t = 0; t < num_stencils && !other_use; ++t)
+        for (int i = 0; i < descs[t].num_grids && !other_use; ++i)
+          other_use = descs[t].grids[i] == descs[s].grids[14] &&
+                      !(descs[t].kind == PSB200_KIND_HIMENO19_GOSA && i == 14);
+      if (other_use) continue;
       for (int t = 0; t < num_stencils; ++t) {
         const bool same = descs[t].kind == PSB200_KIND_HIMENO19_GOSA && plans[t]->himeno && descs[t].num_grids >= 15 &&
                           descs[t].grids[14] == descs[s].grids[14] &&

@@ -266,3 +266,37 @@ def test_plan_cache_iter1_loop_and_invalidation():
         a.free()                           # the next round's grids may reuse these addresses
         b.free()
     api.PSFinalize()
+
+
+def test_residual_emission_is_kept_when_another_stencil_of_the_run_reads_the_grid():
+    """Inside one PSStencilRun a residual-emitting Himeno sweep whose grid a later iteration
+    overwrites runs in its plain form -- but not when another stencil of the same run uses that
+    grid (here a 7-point sweep reads it and feeds p0): the run of 3 iterations must equal three
+    runs of one iteration, bit for bit."""
+    from physis_b200 import api
+    dims = (64, 24, 16)
+    ne = int(np.prod(dims))
+    names = ["p0", "p1", "a0", "a1", "a2", "a3", "b0", "b1", "b2", "c0", "c1", "c2", "bnd", "wrk1", "gosa"]
+    co = [float(np.float32(c)) for c in (0.11, 0.07, 0.13, 0.05, 0.17, 0.03, 0.44)]
+    results = []
+    for split in (False, True):
+        api.PSInit(["t"], 3, dims)
+        rng = np.random.default_rng(12)
+        g = {n: api.Grid(dims, api.PS_FLOAT) for n in names}
+        for n in names[:-1]:
+            g[n].copyin(rng.random(ne, dtype=np.float32) * 0.1)
+        inner = api.PSDomain3DNew(1, dims[0] - 1, 1, dims[1] - 1, 1, dims[2] - 1)
+        whole = api.PSDomain3DNew(0, dims[0], 0, dims[1], 0, dims[2])
+        d = [api.stencil_desc(api.KIND_HIMENO19_GOSA, inner, [g[n] for n in names], [0.8]),
+             api.stencil_desc(api.KIND_DIFFUSION7_CLAMP, whole, [g["gosa"], g["p0"]], co)]
+        if split:
+            for _ in range(3):
+                api.stencil_run(1, d)
+        else:
+            api.stencil_run(3, d)
+        results.append([g[n].copyout() for n in ("p0", "p1", "gosa")])
+        for n in names:
+            g[n].free()
+        api.PSFinalize()
+    for a, b in zip(*results):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
