@@ -576,7 +576,7 @@ std::string TuneKey(int num_stencils, const __PSB200StencilDesc *descs) {
   return k;
 }
 
-std::vector<std::string> TuneForms(int num_stencils, const __PSB200StencilDesc *descs) {
+std::vector<std::string> TuneForms(int num_stencils, const __PSB200StencilDesc *descs, int world) {
   std::vector<std::string> f;
   f.push_back("");  // the defaults
   bool all7 = true, allh = true, allp = true;
@@ -588,8 +588,9 @@ std::vector<std::string> TuneForms(int num_stencils, const __PSB200StencilDesc *
   // z chunks of the fused passes: the planner's cost model (star7_pair.cu) against plain
   // divisions of the planes this rank owns
   auto chunk_forms = [&](const std::string &opt) {
+    // (an even share of the planes, not this rank's own count: every rank must build the same list)
     const Grid *g = Grid::FromHandle(descs[0].grids[0]);
-    const int nz = g->decomposed ? g->nz_loc : g->dim[2];
+    const int nz = g->decomposed ? std::max(1, g->dim[2] / world) : g->dim[2];
     int last = 0;
     for (int d : {2, 4, 8, 16}) {
       const int zc = (nz + d - 1) / d;
@@ -643,7 +644,7 @@ namespace {
 // Runs the trials on the first iterations of this run; returns how many iterations they used.
 int TuneOnRun(Runtime *rt, const std::string &key, int iter, int num_stencils,
               const __PSB200StencilDesc *descs) {
-  const std::vector<std::string> forms = TuneForms(num_stencils, descs);
+  const std::vector<std::string> forms = TuneForms(num_stencils, descs, rt->world());
   const int per_form = kTuneWarm + kTuneTimed;
   if (forms.size() < 2 || iter < (int)forms.size() * per_form + 1) return 0;
   const Options saved = rt->opt;

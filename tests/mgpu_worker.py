@@ -256,7 +256,9 @@ def case_autotune():
     from physis_b200 import api
     co64 = np.array([0.11, 0.07, 0.13, 0.05, 0.17, 0.03, 0.44])
     co = [float(np.float32(c)) for c in co64]
-    for shape in [(128, 32, 16), (512, 12, 24)]:
+    # (the last shape: uneven slabs, 16 and 17 planes on two ranks -- the list of forms, which includes z chunks
+    # derived from the slab thickness, must still be the same on every rank)
+    for shape in [(128, 32, 16), (512, 12, 24), (128, 24, 33)]:
         nx, ny, nz = shape
         api.PSInit(["t"], 3, shape)
         api.set_option("autotune=1")
